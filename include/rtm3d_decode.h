@@ -1,0 +1,144 @@
+/*
+ * rtm3d_decode.h -- C ABI of librtm3d_decode.so: the B200 (sm_100a) replacement of RTM3D's post-head
+ * keypoint-heatmap decoder.
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own; every entry point below replaces a span of
+ * reference Python (cited file:line, relative to hitfeelee/rtm3d) and is what a ctypes binding on the reference
+ * side binds (INTEGRATION.md shows that stub).  Plain pointers and sizes only: no torch types cross this boundary.
+ *
+ * Conventions
+ *  - all map pointers are DEVICE pointers to contiguous NCHW tensors (models/nets/header.py:40-46), dtype
+ *    RTM3D_F32 or RTM3D_BF16 (bf16 is widened exactly to fp32 on load, then the fp32 pipeline is followed bit for bit);
+ *  - outputs are fixed-size [B,K,...] device buffers; rows >= counts[b] are zero (cls/flat = -1);
+ *  - rows are ordered (score desc, flat index asc) with flat = c*H*W + y*W + x -- the order torch.topk yields on
+ *    CUDA (measured) and the one the reference decoder therefore produces in detect.py;
+ *  - the library never allocates, frees, synchronises the host, or keeps pointers after return; work is enqueued
+ *    on `stream` (a cudaStream_t passed as void*);
+ *  - return 0 on success, a negative RTM3D_ERR_* on bad arguments, a positive cudaError_t on launch failure; the
+ *    message is available from rtm3d_last_error() (thread-local).  No exceptions cross the ABI.
+ */
+#ifndef RTM3D_DECODE_H_
+#define RTM3D_DECODE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTM3D_ABI_VERSION 1
+#define RTM3D_MAX_TOPK 1024
+#define RTM3D_MAX_VERTS 16
+
+enum rtm3d_dtype { RTM3D_F32 = 0, RTM3D_BF16 = 1 };
+
+enum rtm3d_error {
+  RTM3D_OK = 0,
+  RTM3D_ERR_NULL = -1,      /* a required pointer is NULL */
+  RTM3D_ERR_SHAPE = -2,     /* B,C,H,W,n_vert out of range */
+  RTM3D_ERR_TOPK = -3,      /* K < 1, K > RTM3D_MAX_TOPK or K > C*H*W */
+  RTM3D_ERR_ALIGN = -4,     /* a base pointer is not aligned to its element size */
+  RTM3D_ERR_WORKSPACE = -5, /* ws_bytes smaller than rtm3d_decode_workspace_bytes() */
+  RTM3D_ERR_DTYPE = -6,     /* unknown dtype */
+  RTM3D_ERR_THRESH = -7,    /* threshold negative or NaN (0.0 fillers could then pass) */
+  RTM3D_ERR_DEVICE = -8     /* no sm_100 device / kernel image unusable on the current device */
+};
+
+/* rtm3d_decode_main flags */
+#define RTM3D_FLAG_FORCE_GENERIC 1u /* use the shape-generic strip kernels even when the streaming kernel applies */
+
+int rtm3d_abi_version(void);
+const char* rtm3d_last_error(void);
+/* static string: compiler, arch and kernel variants built in */
+const char* rtm3d_build_info(void);
+
+/* Bytes of device scratch the decode entry points need for this shape (keys of the per-strip top-K lists and the
+ * per-image tickets).  The scratch must be zeroed ONCE with rtm3d_workspace_init after allocation; every call leaves
+ * it clean again (tickets are reset by the CTA that consumes them). */
+int rtm3d_decode_workspace_bytes(int B, int C, int H, int W, int K, size_t* out_bytes);
+int rtm3d_workspace_init(void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * Tier A -- replaces Model.inference for the main branch (models/model.py:29-75), i.e. _obtain_main_proj2d
+ * (:77-98), utils/model_utils.py:17-26 nms_hm, _obtain_offset_fr_main (:117-132), the sub-pixel add (:48-50) and
+ * the vertex regress / scale / 2D box (:63-73), for the whole batch in one enqueue.
+ *
+ *   hm     [B,C,H,W]        main_kf logits
+ *   off    [B,2*n_vert,H,W] offset_fr_main (channel 2v = dx of vertex v, 2v+1 = dy; raw, no activation)
+ *   off2   [B,2,H,W]        main_offset logits (sigmoid applied after the gather)
+ * outputs (device):
+ *   cls    int64 [B,K]          score f32 [B,K]          proj  f32 [B,K,2]   (x,y in input pixels)
+ *   verts  f32  [B,K,n_vert,2]  bbox  f32 [B,K,4] (xmin,ymin,xmax,ymax)
+ *   flat   int32 [B,K]  (may be NULL) flat peak index c*H*W + y*W + x
+ *   counts int32 [B]    N_b = #{top-K scores > thresh}  (strict >, models/model.py:91)
+ */
+int rtm3d_decode_main(const void* hm, const void* off, const void* off2, int dtype,
+                      int B, int C, int H, int W, int n_vert, int K, float thresh, float down,
+                      int64_t* cls, float* score, float* proj, float* verts, float* bbox,
+                      int32_t* flat, int32_t* counts,
+                      void* ws, size_t ws_bytes, unsigned flags, void* stream);
+
+/*
+ * Same computation for HOST-resident head outputs (the e2e path of bench.py).  `hm_host` is copied to `dev_hm`
+ * (device staging of B*C*H*W elements) with one async copy; `off_host` / `off2_host` must be page-locked, mapped
+ * host memory (cudaHostAlloc / cudaHostRegister): only the K*(2*n_vert+2) scalars per image that the decode needs
+ * are read from them, by the GPU, over PCIe (zero-copy) -- the regression planes are never staged.  Outputs go to
+ * device buffers as above and are then copied to the `*_host` pointers (page-locked) on the same stream.  The call
+ * returns after enqueueing; the caller synchronises the stream.
+ */
+int rtm3d_decode_main_host(const void* hm_host, const void* off_host, const void* off2_host, int dtype,
+                           int B, int C, int H, int W, int n_vert, int K, float thresh, float down,
+                           void* dev_hm,
+                           int64_t* cls, float* score, float* proj, float* verts, float* bbox,
+                           int32_t* flat, int32_t* counts,
+                           int64_t* cls_host, float* score_host, float* proj_host, float* verts_host,
+                           float* bbox_host, int32_t* flat_host, int32_t* counts_host,
+                           void* ws, size_t ws_bytes, unsigned flags, void* stream);
+
+/*
+ * Tier B (dormant in the reference) -- _obtain_vertex_proj2d (models/model.py:100-115) plus the commented sub-pixel
+ * wiring (:52-60): per image AND per channel top-K over H*W, no threshold (0.0-score fillers in ascending index
+ * order when a channel has fewer than K positive peaks).
+ *   kpt_hm [B,Cv,H,W], voff2 [B,2,H,W]
+ *   kscore f32 [B,Cv,K]   kxy f32 [B,Cv,K,2] (x + sigmoid(voff2[0]), y + sigmoid(voff2[1]); heat-map units, unscaled)
+ *   kflat  int32 [B,Cv,K] (y*W + x)
+ */
+int rtm3d_decode_keypoints(const void* kpt_hm, const void* voff2, int dtype,
+                           int B, int Cv, int H, int W, int K,
+                           float* kscore, float* kxy, int32_t* kflat,
+                           void* ws, size_t ws_bytes, unsigned flags, void* stream);
+
+/*
+ * Tier B -- _group_vertexs_kf (models/model.py:134-162): for every detection n of rtm3d_decode_main and keypoint
+ * channel k, j* = argmin_j ||(v_kj - m_n) - off_kn||^2 over the K candidates (first minimal j), with m_n and off_kn
+ * recomputed from `flat` exactly as in Tier A; channels k >= n_vert use a zero offset.
+ *   kpt_proj f32 [B,K,Cv,2] = down * v_kj*    kpt_score f32 [B,K,Cv]    kpt_j int32 [B,K,Cv]
+ *   verts_cv f32 [B,K,Cv,2] = down * (off_kn + m_n)   (may be NULL)
+ */
+int rtm3d_group_vertices(const int32_t* flat, const int32_t* counts,
+                         const void* off, const void* off2, int dtype,
+                         int B, int H, int W, int n_vert, int K,
+                         const float* kscore, const float* kxy, int Cv, float down,
+                         float* kpt_proj, float* kpt_score, int32_t* kpt_j, float* verts_cv, void* stream);
+
+/*
+ * Tier C (NOT in the reference: parity unpinned, the normative text is oracle/box3d_ref.py) -- gather of a
+ * depth/dimension/orientation regression map at the Tier A peaks and closed-form 3D box recovery with the
+ * reference's geometric conventions (utils/model_utils.py:66-76 rotation_matrix, :80-119 create_corners,
+ * :147-152 calc_proj_corners; flat-9 row-major camera matrix, datasets/dataset_reader.py:108).
+ *   reg [B,Creg,H,W] with Creg = 8 (SMOKE style: depth 1, sub-pixel 2, dims 3, sin/cos 2; `mode` 0) or
+ *   Creg = 14 (multi-bin: depth 1, sub-pixel 2, dims 3, bins 8; `mode` 1)
+ *   cam [B,9] (already divided by `down` on entries 0..5 if it is to act on heat-map coordinates)
+ *   dim_ref [C,3] rows (h,w,l); depth_ref = (mu_z, sigma_z)
+ * outputs: loc f32 [B,K,3], dim f32 [B,K,3] (h,w,l), alpha f32 [B,K], rot_y f32 [B,K], corners2d f32 [B,K,8,2]
+ */
+int rtm3d_decode_box3d(const int32_t* flat, const int32_t* counts, const void* reg, int dtype,
+                       int B, int C, int H, int W, int Creg, int K, int mode,
+                       const float* cam, const float* dim_ref, float depth_mu, float depth_sigma,
+                       float* loc, float* dim, float* alpha, float* rot_y, float* corners2d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTM3D_DECODE_H_ */

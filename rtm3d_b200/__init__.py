@@ -1,0 +1,12 @@
+"""rtm3d_b200 -- B200-native (sm_100a) replacement of RTM3D's post-head keypoint-heatmap decoder.
+
+Python/PyTorch owns memory and streams; every arithmetic step runs in hand-written CUDA kernels behind the C ABI of
+``librtm3d_decode.so`` (include/rtm3d_decode.h).  There is no CPU path and no fallback.
+"""
+from ._native import LIB_PATH, build  # noqa: F401
+from .decoder import (GroupedKeypoints, HeatmapDecoder, KeypointCandidates, PackedDetections,  # noqa: F401
+                      decoder_from_config)
+from .plugin import install, uninstall  # noqa: F401
+
+__all__ = ["HeatmapDecoder", "PackedDetections", "KeypointCandidates", "GroupedKeypoints", "decoder_from_config",
+           "install", "uninstall", "build", "LIB_PATH"]

@@ -1,0 +1,209 @@
+// extern "C" boundary of librtm3d_decode.so (include/rtm3d_decode.h): argument validation, workspace carving,
+// launch.  No allocation, no host synchronisation, no state kept after return.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/rtm3d_decode.h"
+#include "params.h"
+#include "postproc.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(int e, const char* what) {
+  if (e == 0) return 0;
+  return fail(e, "%s: %s", what, cudaGetErrorString(static_cast<cudaError_t>(e)));
+}
+
+size_t elem_size(int dtype) { return dtype == RTM3D_F32 ? 4 : 2; }
+
+int check_shape(int B, int C, int H, int W, int K) {
+  if (B < 1 || C < 1 || H < 1 || W < 1 || B > 65535) return fail(RTM3D_ERR_SHAPE, "bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
+  if (static_cast<double>(C) * H * W >= 2147483648.0) return fail(RTM3D_ERR_SHAPE, "C*H*W must be < 2^31");
+  if (W > 16384) return fail(RTM3D_ERR_SHAPE, "W=%d > 16384 unsupported", W);
+  if (K < 1 || K > RTM3D_MAX_TOPK) return fail(RTM3D_ERR_TOPK, "K=%d outside [1,%d]", K, RTM3D_MAX_TOPK);
+  return 0;
+}
+
+// x < t0  =>  computed sigmoid(x) <= thresh (so the strict `score > thresh` of models/model.py:91 fails).
+float prefilter_logit(float thresh) {
+  if (!(thresh > 0.0f)) return -INFINITY;
+  if (thresh >= 1.0f) return INFINITY;
+  const double t = thresh;
+  const double L = std::log(t / (1.0 - t));
+  const double delta = std::ldexp(1.0, -16) / (1.0 - t) + std::ldexp(1.0, -16) * std::fabs(L) + std::ldexp(1.0, -16);
+  const double v = L - delta;
+  float f = static_cast<float>(v);
+  if (static_cast<double>(f) > v) f = std::nextafterf(f, -INFINITY);
+  return f;
+}
+
+void carve(rtm3d::DecodeParams& p, const rtm3d::WorkspaceLayout& L, void* ws) {
+  unsigned char* base = static_cast<unsigned char*>(ws);
+  p.tickets = reinterpret_cast<uint32_t*>(base + L.tickets_off);
+  p.keys = reinterpret_cast<uint64_t*>(base + L.keys_off);
+  p.key_counts = reinterpret_cast<uint32_t*>(base + L.counts_off);
+  p.strip_rows = L.strip_rows;
+  p.nstrips = L.nstrips;
+  p.list_cap = L.list_cap;
+}
+
+int dispatch(const rtm3d::DecodeParams& p, const rtm3d::WorkspaceLayout& L, int dtype, int mode, unsigned flags,
+             cudaStream_t s) {
+  if (!(flags & RTM3D_FLAG_FORCE_GENERIC) && rtm3d::stream_eligible(p, dtype, mode)) {
+    return cuda_fail(rtm3d::launch_stream(p, dtype, mode, s), "decode (streaming kernel) launch");
+  }
+  if (L.generic_smem > 200 * 1024) return fail(RTM3D_ERR_SHAPE, "row too wide for the generic kernel (%zu B smem)", L.generic_smem);
+  return cuda_fail(rtm3d::launch_generic(p, dtype, mode, L.generic_smem, s), "decode (generic kernel) launch");
+}
+
+}  // namespace
+
+extern "C" {
+
+int rtm3d_abi_version(void) { return RTM3D_ABI_VERSION; }
+
+const char* rtm3d_last_error(void) { return g_err; }
+
+const char* rtm3d_build_info(void) {
+  return "librtm3d_decode: nvcc " __VERSION__ " cuda "
+#define RTM3D_STR2(x) #x
+#define RTM3D_STR(x) RTM3D_STR2(x)
+      RTM3D_STR(__CUDACC_VER_MAJOR__) "." RTM3D_STR(__CUDACC_VER_MINOR__)
+      " sm_100a; kernels: decode_stream (cp.async.bulk ring + selector warp), decode_generic (strip/merge),"
+      " group_vertices, box3d; fp32+bf16 inputs";
+}
+
+int rtm3d_decode_workspace_bytes(int B, int C, int H, int W, int K, size_t* out_bytes) {
+  if (!out_bytes) return fail(RTM3D_ERR_NULL, "out_bytes is NULL");
+  if (int e = check_shape(B, C, H, W, K)) return e;
+  *out_bytes = rtm3d::workspace_layout(B, C, H, W, K).total;
+  return 0;
+}
+
+int rtm3d_workspace_init(void* ws, size_t ws_bytes, void* stream) {
+  if (!ws) return fail(RTM3D_ERR_NULL, "ws is NULL");
+  return cuda_fail(static_cast<int>(cudaMemsetAsync(ws, 0, ws_bytes, static_cast<cudaStream_t>(stream))), "workspace memset");
+}
+
+int rtm3d_decode_main(const void* hm, const void* off, const void* off2, int dtype, int B, int C, int H, int W,
+                      int n_vert, int K, float thresh, float down, int64_t* cls, float* score, float* proj,
+                      float* verts, float* bbox, int32_t* flat, int32_t* counts, void* ws, size_t ws_bytes,
+                      unsigned flags, void* stream) {
+  if (!hm || !off || !off2 || !cls || !score || !proj || !verts || !bbox || !counts || !ws)
+    return fail(RTM3D_ERR_NULL, "NULL pointer argument");
+  if (dtype != RTM3D_F32 && dtype != RTM3D_BF16) return fail(RTM3D_ERR_DTYPE, "dtype %d", dtype);
+  if (int e = check_shape(B, C, H, W, K)) return e;
+  if (n_vert < 1 || n_vert > RTM3D_MAX_VERTS) return fail(RTM3D_ERR_SHAPE, "n_vert=%d outside [1,%d]", n_vert, RTM3D_MAX_VERTS);
+  if (static_cast<long long>(K) > static_cast<long long>(C) * H * W) return fail(RTM3D_ERR_TOPK, "K=%d > C*H*W", K);
+  if (!(thresh >= 0.0f)) return fail(RTM3D_ERR_THRESH, "score threshold must be >= 0 (got %g)", thresh);
+  const size_t es = elem_size(dtype);
+  if (reinterpret_cast<uintptr_t>(hm) % es || reinterpret_cast<uintptr_t>(off) % es || reinterpret_cast<uintptr_t>(off2) % es ||
+      reinterpret_cast<uintptr_t>(cls) % 8 || reinterpret_cast<uintptr_t>(ws) % 256)
+    return fail(RTM3D_ERR_ALIGN, "misaligned pointer (maps: element size, cls: 8 B, ws: 256 B)");
+  const rtm3d::WorkspaceLayout L = rtm3d::workspace_layout(B, C, H, W, K);
+  if (ws_bytes < L.total) return fail(RTM3D_ERR_WORKSPACE, "workspace %zu B < required %zu B", ws_bytes, L.total);
+  rtm3d::DecodeParams p{};
+  p.hm = hm; p.off = off; p.off2 = off2;
+  p.B = B; p.C = C; p.H = H; p.W = W; p.n_vert = n_vert; p.K = K;
+  p.thresh = thresh; p.down = down; p.t0 = prefilter_logit(thresh);
+  p.cls = cls; p.score = score; p.proj = proj; p.verts = verts; p.bbox = bbox; p.flat = flat; p.counts = counts;
+  carve(p, L, ws);
+  return dispatch(p, L, dtype, rtm3d::kModeMain, flags, static_cast<cudaStream_t>(stream));
+}
+
+int rtm3d_decode_main_host(const void* hm_host, const void* off_host, const void* off2_host, int dtype, int B, int C,
+                           int H, int W, int n_vert, int K, float thresh, float down, void* dev_hm, int64_t* cls,
+                           float* score, float* proj, float* verts, float* bbox, int32_t* flat, int32_t* counts,
+                           int64_t* cls_host, float* score_host, float* proj_host, float* verts_host, float* bbox_host,
+                           int32_t* flat_host, int32_t* counts_host, void* ws, size_t ws_bytes, unsigned flags,
+                           void* stream) {
+  if (!hm_host || !off_host || !off2_host || !dev_hm || !counts_host) return fail(RTM3D_ERR_NULL, "NULL pointer argument");
+  if (dtype != RTM3D_F32 && dtype != RTM3D_BF16) return fail(RTM3D_ERR_DTYPE, "dtype %d", dtype);
+  if (int e = check_shape(B, C, H, W, K)) return e;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // regression planes stay in host memory: the epilogue gathers K*(2V+2) scalars per image through the mapped pointer
+  void *d_off = nullptr, *d_off2 = nullptr;
+  cudaError_t e = cudaHostGetDevicePointer(&d_off, const_cast<void*>(off_host), 0);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer(&d_off2, const_cast<void*>(off2_host), 0);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(static_cast<int>(e), "off_host/off2_host must be page-locked mapped host memory: %s", cudaGetErrorString(e));
+  }
+  const size_t hm_bytes = static_cast<size_t>(B) * C * H * W * elem_size(dtype);
+  if (int r = cuda_fail(static_cast<int>(cudaMemcpyAsync(dev_hm, hm_host, hm_bytes, cudaMemcpyHostToDevice, s)), "H2D heat-map")) return r;
+  if (int r = rtm3d_decode_main(dev_hm, d_off, d_off2, dtype, B, C, H, W, n_vert, K, thresh, down, cls, score, proj, verts,
+                                bbox, flat, counts, ws, ws_bytes, flags, stream))
+    return r;
+  const size_t n = static_cast<size_t>(B) * K;
+  struct { void* dst; const void* src; size_t bytes; } copies[] = {
+      {counts_host, counts, static_cast<size_t>(B) * 4}, {cls_host, cls, n * 8}, {score_host, score, n * 4},
+      {proj_host, proj, n * 8}, {verts_host, verts, n * static_cast<size_t>(n_vert) * 8}, {bbox_host, bbox, n * 16},
+      {flat_host, flat, n * 4}};
+  for (auto& c : copies) {
+    if (!c.dst || !c.src) continue;
+    if (int r = cuda_fail(static_cast<int>(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, s)), "D2H results")) return r;
+  }
+  return 0;
+}
+
+int rtm3d_decode_keypoints(const void* kpt_hm, const void* voff2, int dtype, int B, int Cv, int H, int W, int K,
+                           float* kscore, float* kxy, int32_t* kflat, void* ws, size_t ws_bytes, unsigned flags,
+                           void* stream) {
+  if (!kpt_hm || !voff2 || !kscore || !kxy || !kflat || !ws) return fail(RTM3D_ERR_NULL, "NULL pointer argument");
+  if (dtype != RTM3D_F32 && dtype != RTM3D_BF16) return fail(RTM3D_ERR_DTYPE, "dtype %d", dtype);
+  if (int e = check_shape(B, Cv, H, W, K)) return e;
+  if (static_cast<long long>(K) > static_cast<long long>(H) * W) return fail(RTM3D_ERR_TOPK, "K=%d > H*W", K);
+  const size_t es = elem_size(dtype);
+  if (reinterpret_cast<uintptr_t>(kpt_hm) % es || reinterpret_cast<uintptr_t>(voff2) % es || reinterpret_cast<uintptr_t>(ws) % 256)
+    return fail(RTM3D_ERR_ALIGN, "misaligned pointer");
+  const rtm3d::WorkspaceLayout L = rtm3d::workspace_layout(B, Cv, H, W, K);
+  if (ws_bytes < L.total) return fail(RTM3D_ERR_WORKSPACE, "workspace %zu B < required %zu B", ws_bytes, L.total);
+  rtm3d::DecodeParams p{};
+  p.hm = kpt_hm; p.off2 = voff2;
+  p.B = B; p.C = Cv; p.H = H; p.W = W; p.n_vert = 0; p.K = K;
+  p.thresh = 0.f; p.down = 1.f; p.t0 = -INFINITY;
+  p.kscore = kscore; p.kxy = kxy; p.kflat = kflat;
+  carve(p, L, ws);
+  return dispatch(p, L, dtype, rtm3d::kModeKpt, flags, static_cast<cudaStream_t>(stream));
+}
+
+int rtm3d_group_vertices(const int32_t* flat, const int32_t* counts, const void* off, const void* off2, int dtype, int B,
+                         int H, int W, int n_vert, int K, const float* kscore, const float* kxy, int Cv, float down,
+                         float* kpt_proj, float* kpt_score, int32_t* kpt_j, float* verts_cv, void* stream) {
+  if (!flat || !counts || !off || !off2 || !kscore || !kxy || !kpt_proj || !kpt_score || !kpt_j)
+    return fail(RTM3D_ERR_NULL, "NULL pointer argument");
+  if (dtype != RTM3D_F32 && dtype != RTM3D_BF16) return fail(RTM3D_ERR_DTYPE, "dtype %d", dtype);
+  if (int e = check_shape(B, Cv, H, W, K)) return e;
+  if (n_vert < 1 || n_vert > RTM3D_MAX_VERTS) return fail(RTM3D_ERR_SHAPE, "n_vert=%d", n_vert);
+  if (static_cast<size_t>(Cv) * K * 8 > 200 * 1024) return fail(RTM3D_ERR_SHAPE, "Cv*K too large for one CTA");
+  rtm3d::GroupParams g{flat, counts, off, off2, B, H, W, n_vert, K, Cv, kscore, kxy, down, kpt_proj, kpt_score, kpt_j, verts_cv};
+  return cuda_fail(rtm3d::launch_group(g, dtype, static_cast<cudaStream_t>(stream)), "group_vertices launch");
+}
+
+int rtm3d_decode_box3d(const int32_t* flat, const int32_t* counts, const void* reg, int dtype, int B, int C, int H, int W,
+                       int Creg, int K, int mode, const float* cam, const float* dim_ref, float depth_mu,
+                       float depth_sigma, float* loc, float* dim, float* alpha, float* rot_y, float* corners2d,
+                       void* stream) {
+  if (!flat || !counts || !reg || !cam || !dim_ref || !loc || !dim || !alpha || !rot_y || !corners2d)
+    return fail(RTM3D_ERR_NULL, "NULL pointer argument");
+  if (dtype != RTM3D_F32 && dtype != RTM3D_BF16) return fail(RTM3D_ERR_DTYPE, "dtype %d", dtype);
+  if (int e = check_shape(B, C, H, W, K)) return e;
+  const bool multibin = (mode & 1) != 0;
+  if (Creg != (multibin ? 14 : 8)) return fail(RTM3D_ERR_SHAPE, "Creg=%d does not match mode %d (8 SMOKE-style, 14 multi-bin)", Creg, mode);
+  rtm3d::Box3dParams q{flat, counts, reg, B, C, H, W, Creg, K, mode, cam, dim_ref, depth_mu, depth_sigma, loc, dim, alpha, rot_y, corners2d};
+  return cuda_fail(rtm3d::launch_box3d(q, dtype, static_cast<cudaStream_t>(stream)), "box3d launch");
+}
+
+}  // extern "C"

@@ -1,0 +1,172 @@
+// Post-selection kernels: keypoint grouping (Tier B, models/model.py:134-162) and closed-form 3D recovery (Tier C).
+#include "common.cuh"
+#include "params.h"
+#include "postproc.h"
+
+namespace rtm3d {
+
+// ---------------------------------------------------------------------------------------------------------------
+// _group_vertexs_kf (models/model.py:134-162).  One CTA per image; thread per (detection n, channel k).
+//   rel  = v_kj - m_n                 (:147)      diff = rel - off_kn        (:149)
+//   dist = diff_x^2 + diff_y^2        (:150)      j*   = argmin_j, first minimal index (:151)
+// m_n and off_kn are recomputed from the flat peak index exactly as the Tier A epilogue does (models/model.py:47-50).
+template <typename T>
+__global__ void __launch_bounds__(256) group_vertices_kernel(const GroupParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* s_xy = reinterpret_cast<float*>(smem_raw);            // [Cv*K*2]
+  const int b = blockIdx.x;
+  const int K = p.K, Cv = p.Cv, HW = p.H * p.W;
+  const int n_det = p.counts[b];
+  const float* kxy = p.kxy + static_cast<size_t>(b) * Cv * K * 2;
+  const float* kscore = p.kscore + static_cast<size_t>(b) * Cv * K;
+  for (int i = threadIdx.x; i < Cv * K * 2; i += blockDim.x) s_xy[i] = kxy[i];
+  __syncthreads();
+  const T* off2 = reinterpret_cast<const T*>(p.off2) + static_cast<size_t>(b) * 2 * HW;
+  const T* off = reinterpret_cast<const T*>(p.off) + static_cast<size_t>(b) * 2 * p.n_vert * HW;
+  for (int w = threadIdx.x; w < K * Cv; w += blockDim.x) {
+    const int n = w / Cv, k = w - n * Cv;
+    const size_t row = (static_cast<size_t>(b) * K + n) * Cv + k;
+    if (n >= n_det) {
+      p.kpt_proj[row * 2] = 0.f; p.kpt_proj[row * 2 + 1] = 0.f;
+      p.kpt_score[row] = 0.f;
+      p.kpt_j[row] = -1;
+      if (p.verts_cv) { p.verts_cv[row * 2] = 0.f; p.verts_cv[row * 2 + 1] = 0.f; }
+      continue;
+    }
+    const int flat = p.flat[static_cast<size_t>(b) * K + n];
+    const int rem = flat % HW;
+    const int yi = rem / p.W, xi = rem - yi * p.W;
+    const float mx = __fadd_rn(static_cast<float>(xi), sigmoid_ref(to_f32(off2[rem])));
+    const float my = __fadd_rn(static_cast<float>(yi), sigmoid_ref(to_f32(off2[HW + rem])));
+    float ox = 0.f, oy = 0.f;
+    if (k < p.n_vert) {
+      ox = to_f32(off[static_cast<size_t>(2 * k) * HW + rem]);
+      oy = to_f32(off[static_cast<size_t>(2 * k + 1) * HW + rem]);
+    }
+    const float* cand = s_xy + static_cast<size_t>(k) * K * 2;
+    float best = INFINITY;
+    int bj = 0;
+    for (int j = 0; j < K; ++j) {
+      const float dx = __fsub_rn(__fsub_rn(cand[2 * j], mx), ox);
+      const float dy = __fsub_rn(__fsub_rn(cand[2 * j + 1], my), oy);
+      const float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+      if (d < best) { best = d; bj = j; }
+    }
+    p.kpt_proj[row * 2] = __fmul_rn(p.down, cand[2 * bj]);
+    p.kpt_proj[row * 2 + 1] = __fmul_rn(p.down, cand[2 * bj + 1]);
+    p.kpt_score[row] = kscore[static_cast<size_t>(k) * K + bj];
+    p.kpt_j[row] = bj;
+    if (p.verts_cv) {
+      p.verts_cv[row * 2] = __fmul_rn(p.down, __fadd_rn(ox, mx));
+      p.verts_cv[row * 2 + 1] = __fmul_rn(p.down, __fadd_rn(oy, my));
+    }
+  }
+}
+
+int launch_group(const GroupParams& p, int dtype, cudaStream_t s) {
+  const size_t smem = static_cast<size_t>(p.Cv) * p.K * 2 * sizeof(float);
+  cudaError_t e;
+  if (dtype == 0) {
+    e = cudaFuncSetAttribute(group_vertices_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    group_vertices_kernel<float><<<p.B, 256, smem, s>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(group_vertices_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    group_vertices_kernel<__nv_bfloat16><<<p.B, 256, smem, s>>>(p);
+  }
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tier C: closed-form 3D box recovery (NOT in the reference; normative text: oracle/box3d_ref.py).
+// Geometry conventions are the reference's: Ry = [[c,0,s],[0,1,0],[-s,0,c]] with |sin|,|cos| < 1e-3 snapped to 0
+// (utils/model_utils.py:66-76), corner order x in {+,-} L/2, y in {+,-} H/2, z in {+,-} W/2 nested in that order
+// (:80-119), uv = (K X)[:2] / (z + 1e-6) (:147-152), flat-9 row-major camera matrix (datasets/dataset_reader.py:108).
+constexpr float kPi = 3.14159265358979323846f;
+
+template <typename T>
+__global__ void __launch_bounds__(128) box3d_kernel(const Box3dParams p) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= p.K) return;
+  const size_t row = static_cast<size_t>(b) * p.K + j;
+  const bool valid = j < p.counts[b];
+  float loc[3] = {0, 0, 0}, dim[3] = {0, 0, 0}, alpha = 0, roty = 0, uv[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) uv[i] = 0.f;
+  if (valid) {
+    const int HW = p.H * p.W;
+    const int flat = p.flat[row];
+    const int cls = flat / HW;
+    const int rem = flat - cls * HW;
+    const int yi = rem / p.W, xi = rem - yi * p.W;
+    const T* reg = reinterpret_cast<const T*>(p.reg) + static_cast<size_t>(b) * p.Creg * HW + rem;
+    float r[14];
+#pragma unroll
+    for (int c = 0; c < 14; ++c) r[c] = (c < p.Creg) ? to_f32(reg[static_cast<size_t>(c) * HW]) : 0.f;
+    const float* cam = p.cam + static_cast<size_t>(b) * 9;
+    const float fx = cam[0], cx = cam[2], fy = cam[4], cy = cam[5];
+    const bool multibin = (p.mode & 1) != 0;
+    const bool sig_sub = (p.mode & 2) != 0;
+    const float u = static_cast<float>(xi) + (sig_sub ? sigmoid_ref(r[1]) : r[1]);
+    const float v = static_cast<float>(yi) + (sig_sub ? sigmoid_ref(r[2]) : r[2]);
+    float z;
+    if (multibin) z = 1.0f / (sigmoid_ref(r[0]) + 1e-6f) - 1.0f;
+    else z = r[0] * p.depth_sigma + p.depth_mu;
+    loc[0] = (u - cx) * z / fx;
+    loc[1] = (v - cy) * z / fy;
+    loc[2] = z;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) dim[d] = expf(sigmoid_ref(r[3 + d]) - 0.5f) * p.dim_ref[cls * 3 + d];
+    if (multibin) {
+      if (r[7] > r[11]) alpha = atan2f(r[8], r[9]) - 0.5f * kPi;
+      else alpha = atan2f(r[12], r[13]) + 0.5f * kPi;
+      roty = alpha + atan2f(u - cx, fx);
+    } else {
+      const float nrm = sqrtf(r[6] * r[6] + r[7] * r[7]);
+      const float o0 = r[6] / nrm, o1 = r[7] / nrm;
+      alpha = atanf(o0 / (o1 + 1e-7f));
+      alpha += (o1 >= 0.f) ? -0.5f * kPi : 0.5f * kPi;
+      roty = alpha + atanf(loc[0] / (loc[2] + 1e-7f));
+    }
+    if (roty > kPi) roty -= 2.0f * kPi;
+    if (roty < -kPi) roty += 2.0f * kPi;
+    float sn = sinf(roty), cs = cosf(roty);
+    if (fabsf(sn) < 1e-3f) sn = 0.f;
+    if (fabsf(cs) < 1e-3f) cs = 0.f;
+    const float hl = 0.5f * dim[2], hh = 0.5f * dim[0], hw = 0.5f * dim[1];  // dims are (h,w,l)
+    int q = 0;
+#pragma unroll
+    for (int i = 1; i >= -1; i -= 2)
+#pragma unroll
+      for (int jj = 1; jj >= -1; jj -= 2)
+#pragma unroll
+        for (int k = 1; k >= -1; k -= 2) {
+          const float X = cs * (hl * i) + sn * (hw * k) + loc[0];
+          const float Y = hh * jj + loc[1];
+          const float Z = -sn * (hl * i) + cs * (hw * k) + loc[2];
+          const float px = cam[0] * X + cam[1] * Y + cam[2] * Z;
+          const float py = cam[3] * X + cam[4] * Y + cam[5] * Z;
+          const float pz = cam[6] * X + cam[7] * Y + cam[8] * Z;
+          uv[2 * q] = px / (pz + 1e-6f);
+          uv[2 * q + 1] = py / (pz + 1e-6f);
+          ++q;
+        }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { p.loc[row * 3 + d] = loc[d]; p.dim[row * 3 + d] = dim[d]; }
+  p.alpha[row] = alpha;
+  p.rot_y[row] = roty;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) p.corners2d[row * 16 + i] = uv[i];
+}
+
+int launch_box3d(const Box3dParams& p, int dtype, cudaStream_t s) {
+  dim3 grid((p.K + 127) / 128, p.B);
+  if (dtype == 0) box3d_kernel<float><<<grid, 128, 0, s>>>(p);
+  else box3d_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace rtm3d

@@ -1,0 +1,27 @@
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rtm3d {
+
+struct GroupParams {
+  const int32_t* flat; const int32_t* counts;
+  const void* off; const void* off2;
+  int B, H, W, n_vert, K, Cv;
+  const float* kscore; const float* kxy;
+  float down;
+  float* kpt_proj; float* kpt_score; int32_t* kpt_j; float* verts_cv;
+};
+
+struct Box3dParams {
+  const int32_t* flat; const int32_t* counts; const void* reg;
+  int B, C, H, W, Creg, K, mode;
+  const float* cam; const float* dim_ref;
+  float depth_mu, depth_sigma;
+  float* loc; float* dim; float* alpha; float* rot_y; float* corners2d;
+};
+
+int launch_group(const GroupParams& p, int dtype, cudaStream_t s);
+int launch_box3d(const Box3dParams& p, int dtype, cudaStream_t s);
+
+}  // namespace rtm3d

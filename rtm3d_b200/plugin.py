@@ -1,0 +1,53 @@
+"""Drop-in installation into the reference (hitfeelee/rtm3d) without editing its files.
+
+``install(Model)`` rebinds two methods of ``models.model.Model``:
+
+* ``inference(self, pred_logits)`` (models/model.py:29-75) -> ``HeatmapDecoder.decode`` with the three scalars read
+  from ``self.config`` exactly where the reference reads them (:41-42, :67, :70);
+* ``forward(self, x)`` (models/model.py:20-27): same dataflow, minus the ``[p.clone() for p in pred_logits]`` of :27 --
+  the clone exists only because the reference decoder mutates its inputs in place (``sigmoid_`` at :48, :85); this
+  decoder never writes to them, so ``pred_logits`` is still returned intact for the loss (train.py:71).
+
+detect.py and the eval loops of train.py / train_multi_gpu.py run unchanged.  ``uninstall(Model)`` restores the originals.
+"""
+from __future__ import annotations
+
+from .decoder import HeatmapDecoder
+
+_ORIG = {}
+
+
+def _decoder_of(model) -> HeatmapDecoder:
+    cfg = model.config
+    key = (float(cfg.DETECTOR.SCORE_THRESH), int(cfg.DETECTOR.TOPK_CANDIDATES), float(cfg.MODEL.DOWN_SAMPLE))
+    dec = model.__dict__.get("_rtm3d_b200_decoder")
+    if dec is None or dec[0] != key:
+        dec = (key, HeatmapDecoder(*key))
+        model.__dict__["_rtm3d_b200_decoder"] = dec
+    return dec[1]
+
+
+def _inference(self, pred_logits):
+    return _decoder_of(self).decode(pred_logits)
+
+
+def _forward(self, x):
+    pred_logits = self.detect_header(self.kfpn_fusion(self.backbone(x)))
+    if self.training:
+        return pred_logits
+    return self.inference(pred_logits), pred_logits
+
+
+def install(model_cls) -> None:
+    """Patch the reference ``Model`` class (pass ``models.model.Model``)."""
+    if model_cls in _ORIG:
+        return
+    _ORIG[model_cls] = (model_cls.inference, model_cls.forward)
+    model_cls.inference = _inference
+    model_cls.forward = _forward
+
+
+def uninstall(model_cls) -> None:
+    orig = _ORIG.pop(model_cls, None)
+    if orig:
+        model_cls.inference, model_cls.forward = orig
