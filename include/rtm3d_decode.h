@@ -47,6 +47,7 @@ enum rtm3d_error {
 
 /* rtm3d_decode_main flags */
 #define RTM3D_FLAG_FORCE_GENERIC 1u /* use the shape-generic strip kernels even when the streaming kernel applies */
+#define RTM3D_FLAG_CLUSTER(s) (((unsigned)(s) & 0xFu) << 8) /* streaming kernel: force s CTAs (1,2,4,8) per image; 0 = auto */
 
 int rtm3d_abi_version(void);
 const char* rtm3d_last_error(void);

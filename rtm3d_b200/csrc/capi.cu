@@ -54,15 +54,19 @@ void carve(rtm3d::DecodeParams& p, const rtm3d::WorkspaceLayout& L, void* ws) {
   p.tickets = reinterpret_cast<uint32_t*>(base + L.tickets_off);
   p.keys = reinterpret_cast<uint64_t*>(base + L.keys_off);
   p.key_counts = reinterpret_cast<uint32_t*>(base + L.counts_off);
+  p.status = reinterpret_cast<uint32_t*>(base + L.status_off);
   p.strip_rows = L.strip_rows;
   p.nstrips = L.nstrips;
   p.list_cap = L.list_cap;
 }
 
-int dispatch(const rtm3d::DecodeParams& p, const rtm3d::WorkspaceLayout& L, int dtype, int mode, unsigned flags,
+int dispatch(rtm3d::DecodeParams& p, const rtm3d::WorkspaceLayout& L, int dtype, int mode, unsigned flags,
              cudaStream_t s) {
-  if (!(flags & RTM3D_FLAG_FORCE_GENERIC) && rtm3d::stream_eligible(p, dtype, mode)) {
-    return cuda_fail(rtm3d::launch_stream(p, dtype, mode, s), "decode (streaming kernel) launch");
+  p.cluster_override = static_cast<int>((flags >> 8) & 0xFu);
+  p.debug = static_cast<int>((flags >> 16) & 0xFu);
+  if (!(flags & RTM3D_FLAG_FORCE_GENERIC)) {
+    const int rc = rtm3d::launch_stream(p, dtype, mode, s);   // -1000: shape (or forced cluster size) not eligible
+    if (rc != -1000) return cuda_fail(rc, "decode (streaming kernel) launch");
   }
   if (L.generic_smem > 200 * 1024) return fail(RTM3D_ERR_SHAPE, "row too wide for the generic kernel (%zu B smem)", L.generic_smem);
   return cuda_fail(rtm3d::launch_generic(p, dtype, mode, L.generic_smem, s), "decode (generic kernel) launch");
@@ -84,6 +88,9 @@ const char* rtm3d_build_info(void) {
       " sm_100a; kernels: decode_stream (cp.async.bulk ring + selector warp), decode_generic (strip/merge),"
       " group_vertices, box3d; fp32+bf16 inputs";
 }
+
+/* developer instrumentation (tools/timeline.py); deliberately absent from include/rtm3d_decode.h */
+void rtm3d_debug_set_timeline(void* dev_u64_16_per_cta) { rtm3d::debug_set_timeline(static_cast<unsigned long long*>(dev_u64_16_per_cta)); }
 
 int rtm3d_decode_workspace_bytes(int B, int C, int H, int W, int K, size_t* out_bytes) {
   if (!out_bytes) return fail(RTM3D_ERR_NULL, "out_bytes is NULL");

@@ -20,6 +20,9 @@ constexpr int kMaxVerts = 16;
 __device__ __forceinline__ float sigmoid_ref(float x) {
   return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
 }
+// Same function, one out-of-line copy: for rare paths, so that they do not bloat the instruction footprint of the kernel
+// (a 137 KB kernel was measured to run its cold paths at instruction-fetch speed).
+static __device__ __noinline__ float sigmoid_cold(float x) { return sigmoid_ref(x); }
 
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
@@ -55,7 +58,7 @@ __device__ __forceinline__ float filter_from_kth_logit(float xk) {
 // ---- block-level primitives (all threads of the block must call) ------------------------------------------------
 
 // In-place descending bitonic sort of a[0..npad), npad a power of two.
-__device__ __forceinline__ void block_bitonic_sort_desc(uint64_t* a, int npad) {
+static __device__ __noinline__ void block_bitonic_sort_desc(uint64_t* a, int npad) {
   for (int k = 2; k <= npad; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int i = threadIdx.x; i < npad; i += blockDim.x) {
@@ -75,7 +78,7 @@ __device__ __forceinline__ void block_bitonic_sort_desc(uint64_t* a, int npad) {
 //   keys : n keys in shared memory (not modified)        out : receives min(n,K) keys, unordered
 //   hist : 256 + 4 words of shared scratch
 // Returns min(n, K).
-__device__ __forceinline__ int block_select_topk(const uint64_t* keys, int n, int K, uint64_t* out, uint32_t* hist) {
+static __device__ __noinline__ int block_select_topk(const uint64_t* keys, int n, int K, uint64_t* out, uint32_t* hist) {
   const int tid = threadIdx.x, nt = blockDim.x;
   if (n <= K) {
     for (int i = tid; i < n; i += nt) out[i] = keys[i];

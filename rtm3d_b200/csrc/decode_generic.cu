@@ -141,7 +141,9 @@ WorkspaceLayout workspace_layout(int B, int C, int H, int W, int K) {
   L.generic_smem = generic_smem_bytes(W, K, L.strip_rows, L.list_cap);
   size_t off = 0;
   L.tickets_off = off;
-  off += ((static_cast<size_t>(B) * C * 4 + 255) / 256) * 256 + 256;
+  off += ((static_cast<size_t>(B) * C * 4 + 255) / 256) * 256;
+  L.status_off = off;
+  off += 256;
   L.keys_off = off;
   off += static_cast<size_t>(B) * C * L.nstrips * K * 8;
   off = (off + 255) / 256 * 256;

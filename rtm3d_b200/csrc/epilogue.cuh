@@ -1,58 +1,81 @@
-// Per-detection epilogues shared by the generic and the streaming decode kernels.
+// Epilogues shared by the generic and the streaming decode kernels.  Out-of-line (one copy per kernel): they run once per
+// image and must not bloat the instruction footprint of the scan loops.
 #pragma once
 #include "common.cuh"
 #include "params.h"
 
 namespace rtm3d {
 
-// Tier A row j of image b (models/model.py:47-50 gather + sub-pixel, :63-73 regress / scale / 2D box).
-// `valid` false -> the row is zero-filled (cls = flat = -1).
+// Tier A rows of image b (models/model.py:47-50 gather + sub-pixel, :63-73 regress / scale / 2D box), run by a whole block.
+// One lane per (detection, vertex): the 2V+2 scattered 4-byte gathers of a detection are issued by neighbouring lanes at
+// the same time (one DRAM round trip instead of a serial chain), the 2D box is a shuffle reduction over the vertex lanes.
+//   sorted : `cnt` keys in descending order.  Rows >= cnt are zero-filled (cls = flat = -1).
 template <typename T>
-__device__ __forceinline__ void emit_main_row(const DecodeParams& p, int b, int j, uint64_t key, bool valid) {
-  const int V = p.n_vert;
-  const size_t row = static_cast<size_t>(b) * p.K + j;
-  float* vout = p.verts + row * V * 2;
-  if (!valid) {
-    p.cls[row] = -1;
-    p.score[row] = 0.f;
-    p.proj[row * 2 + 0] = 0.f; p.proj[row * 2 + 1] = 0.f;
-    for (int v = 0; v < 2 * V; ++v) vout[v] = 0.f;
-    p.bbox[row * 4 + 0] = 0.f; p.bbox[row * 4 + 1] = 0.f; p.bbox[row * 4 + 2] = 0.f; p.bbox[row * 4 + 3] = 0.f;
-    if (p.flat) p.flat[row] = -1;
-    return;
-  }
-  const int HW = p.H * p.W;
-  const uint32_t flat = key_flat(key);
-  const int c = flat / HW;
-  const int rem = flat - c * HW;
-  const int yi = rem / p.W;
-  const int xi = rem - yi * p.W;
-  const size_t pix = static_cast<size_t>(yi) * p.W + xi;
+static __device__ __noinline__ void block_emit_main(const DecodeParams& p, int b, const uint64_t* sorted, int cnt) {
+  const int V = p.n_vert, K = p.K, HW = p.H * p.W;
+  int vp = 1;
+  while (vp < V) vp <<= 1;                       // lanes per detection (power of two <= 16)
+  const int items = K * vp;
+  const int items_pad = (items + 31) & ~31;
   const T* off2 = reinterpret_cast<const T*>(p.off2) + static_cast<size_t>(b) * 2 * HW;
   const T* off = reinterpret_cast<const T*>(p.off) + static_cast<size_t>(b) * 2 * V * HW;
-  // issue every gather before the first use: they are the only uncoalesced loads of the decode
-  float raw[2 * kMaxVerts];
-  const float r0 = to_f32(off2[pix]);
-  const float r1 = to_f32(off2[HW + pix]);
-#pragma unroll 4
-  for (int v = 0; v < 2 * V; ++v) raw[v] = to_f32(off[static_cast<size_t>(v) * HW + pix]);
-  const float mx = __fadd_rn(static_cast<float>(xi), sigmoid_ref(r0));
-  const float my = __fadd_rn(static_cast<float>(yi), sigmoid_ref(r1));
-  float lo_x = INFINITY, lo_y = INFINITY, hi_x = -INFINITY, hi_y = -INFINITY;
-  for (int v = 0; v < V; ++v) {
-    const float vx = __fmul_rn(p.down, __fadd_rn(raw[2 * v], mx));
-    const float vy = __fmul_rn(p.down, __fadd_rn(raw[2 * v + 1], my));
-    vout[2 * v] = vx;
-    vout[2 * v + 1] = vy;
-    lo_x = fminf(lo_x, vx); hi_x = fmaxf(hi_x, vx);
-    lo_y = fminf(lo_y, vy); hi_y = fmaxf(hi_y, vy);
+  for (int idx = threadIdx.x; idx < items_pad; idx += blockDim.x) {
+    const int j = idx / vp, v = idx - j * vp;
+    const bool row_ok = j < K;
+    const bool valid = row_ok && j < cnt;
+    const bool vert = v < V;
+    const size_t row = static_cast<size_t>(b) * K + (row_ok ? j : 0);
+    float vx = 0.f, vy = 0.f, mx = 0.f, my = 0.f;
+    uint32_t flat = 0;
+    int c = 0;
+    uint64_t key = 0;
+    if (valid) {
+      key = sorted[j];
+      flat = key_flat(key);
+      c = flat / HW;
+      const int rem = flat - c * HW;
+      const int yi = rem / p.W;
+      const int xi = rem - yi * p.W;
+      // issue every gather before the first use
+      const float r0 = to_f32(off2[rem]);
+      const float r1 = to_f32(off2[HW + rem]);
+      float ox = 0.f, oy = 0.f;
+      if (vert) {
+        ox = to_f32(off[static_cast<size_t>(2 * v) * HW + rem]);
+        oy = to_f32(off[static_cast<size_t>(2 * v + 1) * HW + rem]);
+      }
+      mx = __fadd_rn(static_cast<float>(xi), sigmoid_ref(r0));
+      my = __fadd_rn(static_cast<float>(yi), sigmoid_ref(r1));
+      vx = __fmul_rn(p.down, __fadd_rn(ox, mx));
+      vy = __fmul_rn(p.down, __fadd_rn(oy, my));
+    }
+    float lo_x = (valid && vert) ? vx : INFINITY, hi_x = (valid && vert) ? vx : -INFINITY;
+    float lo_y = (valid && vert) ? vy : INFINITY, hi_y = (valid && vert) ? vy : -INFINITY;
+    for (int d = 1; d < vp; d <<= 1) {
+      lo_x = fminf(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, d));
+      hi_x = fmaxf(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, d));
+      lo_y = fminf(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, d));
+      hi_y = fmaxf(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, d));
+    }
+    if (!row_ok) continue;
+    if (vert) {
+      float* vout = p.verts + (row * V + v) * 2;
+      vout[0] = valid ? vx : 0.f;
+      vout[1] = valid ? vy : 0.f;
+    }
+    if (v == 0) {
+      p.cls[row] = valid ? c : -1;
+      p.score[row] = valid ? key_score(key) : 0.f;
+      p.proj[row * 2 + 0] = valid ? __fmul_rn(p.down, mx) : 0.f;
+      p.proj[row * 2 + 1] = valid ? __fmul_rn(p.down, my) : 0.f;
+      p.bbox[row * 4 + 0] = valid ? lo_x : 0.f;
+      p.bbox[row * 4 + 1] = valid ? lo_y : 0.f;
+      p.bbox[row * 4 + 2] = valid ? hi_x : 0.f;
+      p.bbox[row * 4 + 3] = valid ? hi_y : 0.f;
+      if (p.flat) p.flat[row] = valid ? static_cast<int32_t>(flat) : -1;
+    }
   }
-  p.cls[row] = c;
-  p.score[row] = key_score(key);
-  p.proj[row * 2 + 0] = __fmul_rn(p.down, mx);
-  p.proj[row * 2 + 1] = __fmul_rn(p.down, my);
-  p.bbox[row * 4 + 0] = lo_x; p.bbox[row * 4 + 1] = lo_y; p.bbox[row * 4 + 2] = hi_x; p.bbox[row * 4 + 3] = hi_y;
-  if (p.flat) p.flat[row] = static_cast<int32_t>(flat);
+  if (threadIdx.x == 0) p.counts[b] = cnt;
 }
 
 // Tier B candidate j of plane (b,c): index split + sub-pixel add (models/model.py:113-114 and the commented :55-57).
@@ -71,20 +94,13 @@ __device__ __forceinline__ void emit_kpt_row(const DecodeParams& p, int b, int c
   p.kflat[row] = static_cast<int32_t>(flat);
 }
 
-// Final stage for one selection problem, run by a whole block.
-//   sorted : shared array holding `cnt` keys sorted descending (capacity >= next_pow2(K))
-//   scratch: shared u32 scratch with >= 3*K + 8 words (only used for kModeKpt fillers)
-// kModeMain: rows 0..cnt-1 valid, rest zero-filled, counts[b] = cnt.
-// kModeKpt : rows cnt..K-1 are 0.0-score fillers = the lowest flat indices that are not positive-score peaks.
-template <typename T, int MODE>
-__device__ __forceinline__ void block_emit(const DecodeParams& p, int b, int c, const uint64_t* sorted, int cnt,
-                                           uint32_t* scratch) {
+// Tier B rows of plane (b,c), run by a whole block.  Rows cnt..K-1 are 0.0-score fillers = the lowest flat indices that
+// are not positive-score peaks (what a top-K over the zero-filled peak map returns).
+//   scratch: shared u32 scratch with >= 3*K + 8 words
+template <typename T>
+static __device__ __noinline__ void block_emit_kpt(const DecodeParams& p, int b, int c, const uint64_t* sorted, int cnt,
+                                                   uint32_t* scratch) {
   const int K = p.K;
-  if (MODE == kModeMain) {
-    for (int j = threadIdx.x; j < K; j += blockDim.x) emit_main_row<T>(p, b, j, j < cnt ? sorted[j] : 0ull, j < cnt);
-    if (threadIdx.x == 0) p.counts[b] = cnt;
-    return;
-  }
   for (int j = threadIdx.x; j < cnt; j += blockDim.x) emit_kpt_row<T>(p, b, c, j, key_score(sorted[j]), key_flat(sorted[j]));
   if (cnt < K) {
     const int HW = p.H * p.W;
@@ -105,6 +121,13 @@ __device__ __forceinline__ void block_emit(const DecodeParams& p, int b, int c, 
     __syncthreads();
     for (int j = cnt + threadIdx.x; j < K; j += blockDim.x) emit_kpt_row<T>(p, b, c, j, 0.0f, fill[j]);
   }
+}
+
+template <typename T, int MODE>
+__device__ __forceinline__ void block_emit(const DecodeParams& p, int b, int c, const uint64_t* sorted, int cnt,
+                                           uint32_t* scratch) {
+  if (MODE == kModeMain) block_emit_main<T>(p, b, sorted, cnt);
+  else block_emit_kpt<T>(p, b, c, sorted, cnt, scratch);
 }
 
 }  // namespace rtm3d

@@ -26,10 +26,13 @@ struct DecodeParams {
   uint32_t* tickets;     // [B*C] zero between calls
   uint64_t* keys;        // [B*C*nstrips][K]
   uint32_t* key_counts;  // [B*C*nstrips]
+  uint32_t* status;      // watchdog word of the streaming kernel (0 = ok)
+  int cluster_override;  // streaming kernel: CTAs per problem (0 = choose)
+  int debug;             // developer switches of the streaming kernel (flags bits 16..19)
 };
 
 struct WorkspaceLayout {
-  size_t tickets_off, keys_off, counts_off, total;
+  size_t tickets_off, status_off, keys_off, counts_off, total;
   int strip_rows, nstrips, list_cap;
   size_t generic_smem;
 };
@@ -42,5 +45,6 @@ int launch_generic(const DecodeParams& p, int dtype, int mode, size_t smem, cuda
 // streaming TMA kernel; returns -1000 when the shape is not eligible (caller falls back to the generic path)
 int launch_stream(const DecodeParams& p, int dtype, int mode, cudaStream_t s);
 bool stream_eligible(const DecodeParams& p, int dtype, int mode);
+void debug_set_timeline(unsigned long long* ptr);  // developer instrumentation, not part of the public ABI
 
 }  // namespace rtm3d

@@ -93,7 +93,8 @@ class HeatmapDecoder:
     """B200 decoder with the reference's three configuration scalars
     (DETECTOR.SCORE_THRESH, DETECTOR.TOPK_CANDIDATES, MODEL.DOWN_SAMPLE -- models/model.py:41-42,67,70)."""
 
-    def __init__(self, score_thresh: float = 0.5, topk: int = 30, down_sample: float = 4.0, force_generic: bool = False):
+    def __init__(self, score_thresh: float = 0.5, topk: int = 30, down_sample: float = 4.0, force_generic: bool = False,
+                 cluster: int = 0):
         if not (score_thresh >= 0):
             raise ValueError("score_thresh must be >= 0: zero-score fillers of the peak map could pass a negative threshold")
         if not (1 <= int(topk) <= 1024):
@@ -101,7 +102,9 @@ class HeatmapDecoder:
         self.score_thresh = float(score_thresh)
         self.topk = int(topk)
         self.down_sample = float(down_sample)
-        self.flags = _native.FLAG_FORCE_GENERIC if force_generic else 0
+        if cluster not in (0, 1, 2, 4, 8):
+            raise ValueError("cluster (CTAs per image of the streaming kernel) must be 0 (auto), 1, 2, 4 or 8")
+        self.flags = (_native.FLAG_FORCE_GENERIC if force_generic else 0) | (cluster << 8)
         self._lib = _native.lib()
         self._ws = {}
 

@@ -17,6 +17,10 @@ from rtm3d_b200 import HeatmapDecoder, synth
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 FLOAT_FIELDS = ("score", "proj", "verts", "bbox")
+# kernel variants: the shape-generic strip kernels, the streaming kernel with its own choice of cluster size (falls
+# back to generic on ineligible shapes), and the streaming kernel forced to 1/2/4/8 CTAs per image
+VARIANTS = [dict(force_generic=True), dict(), dict(cluster=1), dict(cluster=2), dict(cluster=4), dict(cluster=8)]
+VARIANT_IDS = ["generic", "auto", "c1", "c2", "c4", "c8"]
 
 
 def _rows(packed, b):
@@ -42,7 +46,7 @@ def _check_padding(packed):
 def _run_exact(logits_cpu, K, thresh, force_generic, dtype=torch.float32, what=""):
     logits = [t.to(DEV).to(dtype).contiguous() for t in logits_cpu]
     before = [t.clone() for t in logits]
-    dec = HeatmapDecoder(thresh, K, 4.0, force_generic=force_generic)
+    dec = HeatmapDecoder(thresh, K, 4.0, **force_generic)
     packed = dec.decode_packed(logits)
     torch.cuda.synchronize()
     for a, b_ in zip(before, logits):
@@ -75,7 +79,7 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("force_generic", [True, False], ids=["generic", "auto"])
+@pytest.mark.parametrize("force_generic", VARIANTS, ids=VARIANT_IDS)
 @pytest.mark.parametrize("kind", synth.KINDS)
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
 def test_vs_cuda_oracle_exact(shape, kind, force_generic):
@@ -84,7 +88,7 @@ def test_vs_cuda_oracle_exact(shape, kind, force_generic):
     _run_exact(logits, K, 0.4, force_generic, what=f"{kind} {shape}")
 
 
-@pytest.mark.parametrize("force_generic", [True, False], ids=["generic", "auto"])
+@pytest.mark.parametrize("force_generic", VARIANTS, ids=VARIANT_IDS)
 @pytest.mark.parametrize("thresh", [0.0, 0.05, 0.4, 0.9, 0.999])
 def test_thresholds_exact(thresh, force_generic):
     logits, _ = synth.head_outputs(3, 3, 48, 80, seed=77, kind="trained")
@@ -93,21 +97,21 @@ def test_thresholds_exact(thresh, force_generic):
     _run_exact(logits, 100, thresh, force_generic, what=f"thresh {thresh}")
 
 
-@pytest.mark.parametrize("force_generic", [True, False], ids=["generic", "auto"])
+@pytest.mark.parametrize("force_generic", VARIANTS, ids=VARIANT_IDS)
 @pytest.mark.parametrize("K", [1, 30, 50, 100, 128, 256, 1024])
 def test_topk_sizes_exact(K, force_generic):
     logits, _ = synth.head_outputs(2, 3, 96, 320, seed=5, kind="randn")
     _run_exact(logits, K, 0.4, force_generic, what=f"K {K}")
 
 
-@pytest.mark.parametrize("force_generic", [True, False], ids=["generic", "auto"])
+@pytest.mark.parametrize("force_generic", VARIANTS, ids=VARIANT_IDS)
 @pytest.mark.parametrize("kind", ["randn", "trained", "quant"])
 def test_bf16_inputs_follow_fp32_pipeline(kind, force_generic):
     logits, _ = synth.head_outputs(2, 3, 96, 320, seed=9, kind=kind)
     _run_exact(logits, 50, 0.4, force_generic, dtype=torch.bfloat16, what=f"bf16 {kind}")
 
 
-@pytest.mark.parametrize("force_generic", [True, False], ids=["generic", "auto"])
+@pytest.mark.parametrize("force_generic", VARIANTS, ids=VARIANT_IDS)
 def test_adversarial_saturated_plateaus(force_generic):
     """All-equal saturated maps: every pixel is a peak with score 1.0, top-K = the K lowest flat indices."""
     logits, _ = synth.head_outputs(2, 3, 24, 40, seed=3, kind="randn")
@@ -122,12 +126,12 @@ def test_adversarial_saturated_plateaus(force_generic):
 
 
 @pytest.mark.parametrize("name", sorted(n for n, c in golden_io.CASES.items() if not c["kpt"]))
-@pytest.mark.parametrize("force_generic", [True, False], ids=["generic", "auto"])
+@pytest.mark.parametrize("force_generic", VARIANTS, ids=VARIANT_IDS)
 def test_vs_golden_reference_outputs(name, force_generic):
     c = golden_io.CASES[name]
     logits_cpu, _ = golden_io.inputs(name)
     gold = golden_io.arrays(name)
-    dec = HeatmapDecoder(c["thresh"], c["K"], c["down"], force_generic=force_generic)
+    dec = HeatmapDecoder(c["thresh"], c["K"], c["down"], **force_generic)
     packed = dec.decode_packed([t.to(DEV) for t in logits_cpu])
     torch.cuda.synchronize()
     swaps = 0
