@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- decoded images/sec of the RTM3D keypoint-heatmap decode path on B200 (+ fraction of the HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4] [--impl b200|reference]
+
+A "step" = one pass of the hot path (Tier A main decode + Tier B keypoint decode + grouping; models/model.py:29-162)
+over one batch of synthetic head outputs that are already resident in HBM.  The default workload is BASELINE.json
+configs[3] ("cfg4": 256 images per GPU, 3x96x320 main heat-map + 9-keypoint heat-map + the 16/2/2-channel regression
+maps, K=100, thresh 0.4), the configuration the metric's "1/2/4/8 B200" is quoted on; per-GPU work is fixed as N
+grows (weak scaling, images are independent: SURVEY.md 8e) and for N > 1 the step ends with the NCCL all-gather of
+the fixed-size detections.  One JSON line is printed by rank 0 (contract in the task statement):
+
+  value        whole-job images/s, device-timed (CUDA events around exactly K steps, max over ranks)
+  roofline     dominant kernel: ALGORITHMIC bytes per launch / its CUDA-event duration vs MEASURED_PEAKS.json hbm_gbs
+  e2e          same metric through the host-buffer C-ABI entry points (pinned host in -> pinned host out, H2D + D2H
+               inside the timed region)
+  cpu_baseline the oracle's torch port of the reference decoder on the box's host cores (bounded sample), rank 0 only
+  clocks       SM clock / throttle reasons sampled with NVML while the timed region runs
+
+`--impl reference` times the reference's CPU implementation of the same path (oracle port: the reference is Python and
+does not travel to the GPU box) on a bounded sample per step and prints the same line with
+"impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "decoded images/sec"
+UNIT = "images/s"
+THRESH, DOWN = 0.4, 4.0
+CPU_SAMPLE_IMAGES = 16          # bounded CPU sample per step of the reference arm / cpu_baseline leg
+
+WORKLOADS = {
+    # name: B per GPU, C, H, W, K, keypoint channels
+    "cfg2": dict(B=32, C=3, H=96, W=320, K=50, kpt=9, note="BASELINE configs[1]: DLA-34 head outputs batch 32, K=50"),
+    "cfg3": dict(B=64, C=3, H=96, W=320, K=100, kpt=0, note="BASELINE configs[2]: centre-keypoint decode batch 64, K=100 (main branch only)"),
+    "cfg4": dict(B=256, C=3, H=96, W=320, K=100, kpt=9, note="BASELINE configs[3]: ResNet-18 head outputs batch 256 per GPU, K=100, main + 9-kpt heat-map"),
+    "cfg4main": dict(B=256, C=3, H=96, W=320, K=100, kpt=0, note="BASELINE configs[3], main branch only (what the reference's inference() runs today)"),
+    "cfg5": dict(B=128, C=3, H=192, W=640, K=100, kpt=9, note="BASELINE configs[4]: 192x640 heat-maps batch 128 per GPU, K=100, main + 9-kpt heat-map"),
+}
+
+
+def algorithmic_bytes_per_image(w, elem=4, n_vert=8):
+    """A = C_hm*H*W*e + K*C_reg*32 + out (gathers charged one 32-byte sector per scalar; regression planes
+    are NOT counted in full).  Returns (total, main part, keypoint part)."""
+    HW, K, Cv = w["H"] * w["W"], w["K"], w["kpt"]
+    main = w["C"] * HW * elem + K * (2 * n_vert + 2) * 32 + K * 100 + 4
+    kpt = (Cv * HW * elem + Cv * K * 2 * 32 + K * Cv * 12) if Cv else 0
+    return main + kpt, main, kpt
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons of one GPU, sampled through NVML while the bench runs."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index, uuid=None):
+        super().__init__(daemon=True)
+        self.index, self.uuid, self.samples, self._stop_evt, self.error = index, uuid, [], threading.Event(), None
+        self.max_mhz = None
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(self.uuid.encode() if isinstance(self.uuid, str) else self.uuid)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self._stop_evt.is_set():
+                mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                try:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((time.perf_counter(), mhz, rs))
+                time.sleep(0.002)
+        except Exception as e:  # NVML missing: report, do not fail the bench
+            self.error = repr(e)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+
+    def summary(self, t0, t1):
+        inside = [s for s in self.samples if t0 <= s[0] <= t1]
+        window = "timed region"
+        if not inside:                      # region shorter than one NVML poll: use every sample taken under load
+            inside, window = self.samples, "whole bench (timed region shorter than one NVML poll)"
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "error": self.error or "no samples"}
+        mhz = sorted(s[1] for s in inside)
+        bits = 0
+        for s in inside:
+            bits |= s[2]
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": self.max_mhz, "samples": len(inside), "window": window,
+                "reasons": sorted(n for b, n in self.REASONS.items() if bits & b)}
+
+
+def make_inputs(torch, w, device, seed, kind="randn"):
+    """every head map torch.randn from a seeded generator on the owning device."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    B, C, H, W = w["B"], w["C"], w["H"], w["W"]
+    mk = lambda c: torch.randn((B, c, H, W), generator=g, device=device, dtype=torch.float32)
+    logits = [mk(C), mk(16), mk(2), mk(2)]
+    kpt = mk(w["kpt"]) if w["kpt"] else None
+    return logits, kpt
+
+
+def cpu_reference_step(torch, decode_ref, logits, kpt, K):
+    """The reference's eval forward after the heads: clone the maps (models/model.py:27), decode (:29-75 + Tier B wiring)."""
+    cl = [p.clone() for p in logits]
+    return decode_ref.decode(cl, THRESH, K, DOWN, None if kpt is None else kpt.clone())
+
+
+def time_cpu_reference(torch, w, steps, warmup, seed=1234):
+    """images/s of the oracle's torch port on the host cores, on a bounded sample of the workload."""
+    from oracle import decode_ref  # bench.py's cpu_baseline / reference arm: the one place the product side may run oracle/
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ws = dict(w, B=min(w["B"], CPU_SAMPLE_IMAGES))
+    logits, kpt = make_inputs(torch, ws, torch.device("cpu"), seed)
+    with torch.no_grad():
+        for _ in range(warmup):
+            cpu_reference_step(torch, decode_ref, logits, kpt, w["K"])
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cpu_reference_step(torch, decode_ref, logits, kpt, w["K"])
+        dt = time.perf_counter() - t0
+    return ws["B"] * steps / dt, dt / steps * 1e3, cores, torch.get_num_threads(), ws["B"]
+
+
+def config_dict(name, w, n_gpus):
+    return {"workload": f"{name}: {w['note']}", "images_per_gpu": w["B"], "global_images": w["B"] * n_gpus,
+            "heatmap": [w["C"], w["H"], w["W"]], "kpt_channels": w["kpt"], "topk": w["K"], "score_thresh": THRESH,
+            "down_sample": DOWN, "parallelism": f"image-sharded x{n_gpus}"}
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    ips, ms, cores, threads, nb = time_cpu_reference(torch, w, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": round(ips, 2), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_dict(args.workload, w, args.gpus),
+            "cpu_baseline": {"value": round(ips, 2), "unit": UNIT, "cores": cores, "kind": "port", "torch_threads": threads,
+                             "sample": f"{nb} images of the workload per step (torch port of Model.inference incl. the clone of "
+                                       f"models/model.py:27 and the keypoint branch when the workload has one), {args.steps} steps"},
+            "e2e": {"value": round(ips, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_b200(args, w):
+    import torch
+    import torch.distributed as dist
+    from rtm3d_b200 import HeatmapDecoder, HostDecodeSession
+    from rtm3d_b200.sharding import gather_detections
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (rtm3d_b200 has no CPU path; use --impl reference for the CPU arm)")
+    if world != args.gpus:
+        raise SystemExit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch N>1 with torch.distributed.run")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    K, B, Cv = w["K"], w["B"], w["kpt"]
+    dec = HeatmapDecoder(THRESH, K, DOWN)
+    nsets = 2
+    sets = [make_inputs(torch, w, dev, 1234 + rank + 100 * s) for s in range(nsets)]
+    heat_bytes = B * (w["C"] + Cv) * w["H"] * w["W"] * 4
+    launches_per_step = 3 if Cv else 1
+
+    gather_out = None
+
+    def step(i, marks=None):
+        logits, kpt = sets[i % nsets]
+        if Cv:
+            det, cand, grp = dec.decode_with_keypoints(logits, kpt, marks=marks)
+        else:
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True); e.record(); marks.append(e)
+            det = dec.decode_packed(logits)
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True); e.record(); marks.append(e)
+            grp = None
+        if world > 1:
+            # the path's one collective: all-gather of the fixed-size detections, on the decode stream
+            nonlocal gather_out
+            if gather_out is None:
+                wire = det.to_wire()
+                gather_out = (torch.empty((world * B,) + tuple(wire.shape[1:]), dtype=wire.dtype, device=dev),
+                              torch.empty((world * B,), dtype=torch.int32, device=dev))
+            gather_detections(det, out=gather_out)
+        return det, grp
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local, uuid="GPU-" + str(torch.cuda.get_device_properties(dev).uuid))
+    sampler.start()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    # ---- timed region: exactly K steps, CUDA events on the launching stream, per-kernel marks on the same stream
+    marks = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        step(i, marks)
+    e1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+
+    # per-kernel durations from the marks (each step: before, after main, [after kpt, after group])
+    per = launches_per_step + 1
+    names = ["decode_main", "decode_keypoints", "group_vertices"][:launches_per_step]
+    kernel_ms = {n: 0.0 for n in names}
+    for s in range(args.steps):
+        for j, n in enumerate(names):
+            kernel_ms[n] += marks[s * per + j].elapsed_time(marks[s * per + j + 1])
+    kernel_ms = {n: v / args.steps for n, v in kernel_ms.items()}
+
+    # ---- end to end: pinned host buffers in, pinned host buffers out, through the host-buffer C-ABI entry points
+    host_logits = [t.to("cpu").pin_memory() for t in sets[0][0]]
+    host_kpt = sets[0][1].to("cpu").pin_memory() if Cv else None
+    sess = HostDecodeSession(dec, B, w["C"], w["H"], w["W"], n_vert=8, kpt_channels=Cv, device=dev)
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        sess.run(host_logits, host_kpt, sync=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        det_h, grp_h = sess.run(host_logits, host_kpt, sync=True)
+        _ = int(det_h.counts[0])     # the result is read on the host
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    sampler.stop()
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        A, A_main, A_kpt = algorithmic_bytes_per_image(w)
+        dom = max(kernel_ms, key=kernel_ms.get)
+        dom_bytes = B * (A_kpt if dom == "decode_keypoints" else A_main if dom == "decode_main" else 0)
+        achieved = dom_bytes / (kernel_ms[dom] * 1e-3) / 1e9 if kernel_ms[dom] > 0 else 0.0
+        step_gbs = B * A / (ms_step * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": round(B * world / (ms_step * 1e-3), 1), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 5), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(config_dict(args.workload, w, world),
+                           l2=f"{nsets} input sets rotated, {heat_bytes / 1e6:.0f} MB of heat-map per step vs 126 MB L2"
+                              + ("" if heat_bytes > 130e6 else " (SMALLER than L2: later steps may hit L2)")),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "bytes_per_launch": dom_bytes, "kernel_ms": {k: round(v, 5) for k, v in kernel_ms.items()},
+                         "step_achieved": round(step_gbs, 1), "step_frac": round(step_gbs / peak, 4),
+                         "algorithmic_bytes_per_image": A},
+            "e2e": {"value": round(B * world * e2e_steps / e2e_s, 1), "unit": UNIT, "h2d_bytes_per_step": sess.h2d_bytes(),
+                    "d2h_bytes_per_step": sess.d2h_bytes(), "steps": e2e_steps,
+                    "api": "HostDecodeSession.run -> rtm3d_decode_main_host / rtm3d_decode_keypoints_host"},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": sampler.summary(t_wall0, t_wall1),
+        }
+        if not args.no_cpu_baseline:
+            ips, ms, cores, threads, nb = time_cpu_reference(torch, w, steps=3, warmup=1)
+            line["cpu_baseline"] = {"value": round(ips, 2), "unit": UNIT, "cores": cores, "kind": "port", "torch_threads": threads,
+                                    "sample": f"{nb} images of the workload, 1 warm-up + 3 timed passes of the torch port of "
+                                              "Model.inference (incl. the clone of models/model.py:27 and the keypoint branch)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg4")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, w)
+    return run_b200(args, w)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -111,6 +111,18 @@ int rtm3d_decode_keypoints(const void* kpt_hm, const void* voff2, int dtype,
                            void* ws, size_t ws_bytes, unsigned flags, void* stream);
 
 /*
+ * rtm3d_decode_keypoints for HOST-resident maps, the Tier B sibling of rtm3d_decode_main_host: `kpt_hm_host` is copied
+ * to the device staging buffer `dev_kpt` (B*Cv*H*W elements), `voff2_host` must be page-locked mapped host memory (only
+ * Cv*K*2 scalars per image are read from it, zero-copy), results are copied to the page-locked `*_host` pointers (any
+ * of which may be NULL) on the same stream.
+ */
+int rtm3d_decode_keypoints_host(const void* kpt_hm_host, const void* voff2_host, int dtype,
+                                int B, int Cv, int H, int W, int K, void* dev_kpt,
+                                float* kscore, float* kxy, int32_t* kflat,
+                                float* kscore_host, float* kxy_host, int32_t* kflat_host,
+                                void* ws, size_t ws_bytes, unsigned flags, void* stream);
+
+/*
  * Tier B -- _group_vertexs_kf (models/model.py:134-162): for every detection n of rtm3d_decode_main and keypoint
  * channel k, j* = argmin_j ||(v_kj - m_n) - off_kn||^2 over the K candidates (first minimal j), with m_n and off_kn
  * recomputed from `flat` exactly as in Tier A; channels k >= n_vert use a zero offset.

@@ -4,9 +4,9 @@ Python/PyTorch owns memory and streams; every arithmetic step runs in hand-writt
 ``librtm3d_decode.so`` (include/rtm3d_decode.h).  There is no CPU path and no fallback.
 """
 from ._native import LIB_PATH, build  # noqa: F401
-from .decoder import (GroupedKeypoints, HeatmapDecoder, KeypointCandidates, PackedDetections,  # noqa: F401
+from .decoder import (GroupedKeypoints, HeatmapDecoder, HostDecodeSession, KeypointCandidates, PackedDetections,  # noqa: F401
                       decoder_from_config)
 from .plugin import install, uninstall  # noqa: F401
 
-__all__ = ["HeatmapDecoder", "PackedDetections", "KeypointCandidates", "GroupedKeypoints", "decoder_from_config",
+__all__ = ["HeatmapDecoder", "PackedDetections", "KeypointCandidates", "GroupedKeypoints", "HostDecodeSession", "decoder_from_config",
            "install", "uninstall", "build", "LIB_PATH"]

@@ -186,6 +186,33 @@ int rtm3d_decode_keypoints(const void* kpt_hm, const void* voff2, int dtype, int
   return dispatch(p, L, dtype, rtm3d::kModeKpt, flags, static_cast<cudaStream_t>(stream));
 }
 
+int rtm3d_decode_keypoints_host(const void* kpt_hm_host, const void* voff2_host, int dtype, int B, int Cv, int H, int W,
+                                int K, void* dev_kpt, float* kscore, float* kxy, int32_t* kflat, float* kscore_host,
+                                float* kxy_host, int32_t* kflat_host, void* ws, size_t ws_bytes, unsigned flags,
+                                void* stream) {
+  if (!kpt_hm_host || !voff2_host || !dev_kpt) return fail(RTM3D_ERR_NULL, "NULL pointer argument");
+  if (dtype != RTM3D_F32 && dtype != RTM3D_BF16) return fail(RTM3D_ERR_DTYPE, "dtype %d", dtype);
+  if (int e = check_shape(B, Cv, H, W, K)) return e;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  void* d_voff2 = nullptr;
+  cudaError_t e = cudaHostGetDevicePointer(&d_voff2, const_cast<void*>(voff2_host), 0);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(static_cast<int>(e), "voff2_host must be page-locked mapped host memory: %s", cudaGetErrorString(e));
+  }
+  const size_t hm_bytes = static_cast<size_t>(B) * Cv * H * W * elem_size(dtype);
+  if (int r = cuda_fail(static_cast<int>(cudaMemcpyAsync(dev_kpt, kpt_hm_host, hm_bytes, cudaMemcpyHostToDevice, s)), "H2D keypoint heat-map")) return r;
+  if (int r = rtm3d_decode_keypoints(dev_kpt, d_voff2, dtype, B, Cv, H, W, K, kscore, kxy, kflat, ws, ws_bytes, flags, stream)) return r;
+  const size_t n = static_cast<size_t>(B) * Cv * K;
+  struct { void* dst; const void* src; size_t bytes; } copies[] = {
+      {kscore_host, kscore, n * 4}, {kxy_host, kxy, n * 8}, {kflat_host, kflat, n * 4}};
+  for (auto& c : copies) {
+    if (!c.dst) continue;
+    if (int r = cuda_fail(static_cast<int>(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, s)), "D2H keypoint results")) return r;
+  }
+  return 0;
+}
+
 int rtm3d_group_vertices(const int32_t* flat, const int32_t* counts, const void* off, const void* off2, int dtype, int B,
                          int H, int W, int n_vert, int K, const float* kscore, const float* kxy, int Cv, float down,
                          float* kpt_proj, float* kpt_score, int32_t* kpt_j, float* verts_cv, void* stream) {

@@ -216,12 +216,24 @@ class HeatmapDecoder:
         _native.check(rc, "rtm3d_group_vertices")
         return out
 
-    def decode_with_keypoints(self, pred_logits, kpt_logits):
+    def decode_with_keypoints(self, pred_logits, kpt_logits, marks=None):
         """Tier A + Tier B as the commented wiring of models/model.py:45-62,68-69 describes.  Returns
-        (PackedDetections, KeypointCandidates, GroupedKeypoints), all asynchronous."""
+        (PackedDetections, KeypointCandidates, GroupedKeypoints), all asynchronous.  ``marks``: optional list that
+        receives a recorded ``torch.cuda.Event`` before the first and after each of the three launches (bench.py times
+        the individual kernels with it)."""
+        def mark():
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append(e)
+        mark()
         det = self.decode_packed(pred_logits)
+        mark()
         cand = self.decode_keypoints(kpt_logits, pred_logits[3])
-        return det, cand, self.group_keypoints(det, cand, pred_logits)
+        mark()
+        grp = self.group_keypoints(det, cand, pred_logits)
+        mark()
+        return det, cand, grp
 
     # ------------------------------------------------------------------ Tier C
     def decode_box3d(self, det: PackedDetections, reg: torch.Tensor, cam: torch.Tensor, dim_ref: torch.Tensor,
@@ -249,6 +261,90 @@ class HeatmapDecoder:
         _native.check(rc, "rtm3d_decode_box3d")
         out["_keepalive"] = (cam, dim_ref)
         return out
+
+
+class HostDecodeSession:
+    """End-to-end path for HOST-resident head outputs (what a caller outside the training process has): page-locked
+    host tensors in, page-locked host tensors out, through ``rtm3d_decode_main_host`` / ``rtm3d_decode_keypoints_host``.
+
+    Per step the heat-maps (main, and the keypoint heat-map when given) cross PCIe once; the regression maps stay in
+    host memory and only the K*(2V+2) (+ Cv*K*2) scalars the decode needs are read from them by the GPU (zero-copy).
+    Buffers are allocated once; ``run`` enqueues everything on the current stream and returns the host result buffers,
+    valid after the stream is synchronised (``run(..., sync=True)`` does that)."""
+
+    def __init__(self, dec: HeatmapDecoder, B, C, H, W, n_vert=8, kpt_channels=0, dtype=torch.float32, device="cuda:0"):
+        self.dec, self.shape, self.V, self.Cv, self.dtype = dec, (B, C, H, W), n_vert, kpt_channels, dtype
+        self.dev = torch.device(device)
+        K = dec.topk
+        d = lambda *sh, dt=torch.float32: torch.empty(sh, dtype=dt, device=self.dev)
+        h = lambda *sh, dt=torch.float32: torch.empty(sh, dtype=dt, pin_memory=True)
+        self.dev_hm = d(B, C, H, W, dt=dtype)
+        self.det = PackedDetections(cls=d(B, K, dt=torch.int64), score=d(B, K), proj=d(B, K, 2), verts=d(B, K, n_vert, 2),
+                                    bbox=d(B, K, 4), flat=d(B, K, dt=torch.int32), counts=d(B, dt=torch.int32))
+        self.det_host = PackedDetections(cls=h(B, K, dt=torch.int64), score=h(B, K), proj=h(B, K, 2), verts=h(B, K, n_vert, 2),
+                                         bbox=h(B, K, 4), flat=h(B, K, dt=torch.int32), counts=h(B, dt=torch.int32))
+        self.cand = self.grp = self.grp_host = self.dev_kpt = None
+        if kpt_channels:
+            Cv = kpt_channels
+            self.dev_kpt = d(B, Cv, H, W, dt=dtype)
+            self.cand = KeypointCandidates(score=d(B, Cv, K), xy=d(B, Cv, K, 2), flat=d(B, Cv, K, dt=torch.int32))
+            self.grp = GroupedKeypoints(kpt_proj=d(B, K, Cv, 2), kpt_score=d(B, K, Cv), kpt_j=d(B, K, Cv, dt=torch.int32),
+                                        verts=d(B, K, Cv, 2))
+            self.grp_host = GroupedKeypoints(kpt_proj=h(B, K, Cv, 2), kpt_score=h(B, K, Cv),
+                                             kpt_j=h(B, K, Cv, dt=torch.int32), verts=h(B, K, Cv, 2))
+
+    def h2d_bytes(self) -> int:
+        n = self.dev_hm.numel() * self.dev_hm.element_size()
+        if self.dev_kpt is not None:
+            n += self.dev_kpt.numel() * self.dev_kpt.element_size()
+        return n
+
+    def d2h_bytes(self) -> int:
+        t = [self.det_host.cls, self.det_host.score, self.det_host.proj, self.det_host.verts, self.det_host.bbox,
+             self.det_host.flat, self.det_host.counts]
+        if self.grp_host is not None:
+            t += [self.grp_host.kpt_proj, self.grp_host.kpt_score, self.grp_host.kpt_j, self.grp_host.verts]
+        return sum(x.numel() * x.element_size() for x in t)
+
+    def run(self, pred_logits_host, kpt_host=None, sync=True):
+        dec, lib = self.dec, self.dec._lib
+        B, C, H, W = self.shape
+        K, V = dec.topk, self.V
+        main, off, off2, voff2 = pred_logits_host
+        for t in (main, off, off2, voff2) + ((kpt_host,) if kpt_host is not None else ()):
+            if t.is_cuda or not t.is_pinned() or not t.is_contiguous():
+                raise ValueError("HostDecodeSession.run expects contiguous page-locked host tensors")
+        dt = _dtype_code(main)
+        with torch.cuda.device(self.dev):
+            ws, stream = dec._workspace(self.dev, B, C, H, W)
+            p, ph = self.det, self.det_host
+            _native.check(lib.rtm3d_decode_main_host(
+                main.data_ptr(), off.data_ptr(), off2.data_ptr(), dt, B, C, H, W, V, K, dec.score_thresh, dec.down_sample,
+                self.dev_hm.data_ptr(), p.cls.data_ptr(), p.score.data_ptr(), p.proj.data_ptr(), p.verts.data_ptr(),
+                p.bbox.data_ptr(), p.flat.data_ptr(), p.counts.data_ptr(),
+                ph.cls.data_ptr(), ph.score.data_ptr(), ph.proj.data_ptr(), ph.verts.data_ptr(), ph.bbox.data_ptr(),
+                ph.flat.data_ptr(), ph.counts.data_ptr(), ws.data_ptr(), ws.numel(), dec.flags, stream),
+                "rtm3d_decode_main_host")
+            if kpt_host is not None:
+                Cv = self.Cv
+                ws2, _ = dec._workspace(self.dev, B, Cv, H, W)
+                c = self.cand
+                _native.check(lib.rtm3d_decode_keypoints_host(
+                    kpt_host.data_ptr(), voff2.data_ptr(), dt, B, Cv, H, W, K, self.dev_kpt.data_ptr(),
+                    c.score.data_ptr(), c.xy.data_ptr(), c.flat.data_ptr(), None, None, None,
+                    ws2.data_ptr(), ws2.numel(), dec.flags, stream), "rtm3d_decode_keypoints_host")
+                g, gh = self.grp, self.grp_host
+                # pinned host memory is mapped into the device address space (UVA): the grouping kernel re-reads the
+                # K*(2V+2) regression scalars straight from host memory
+                _native.check(lib.rtm3d_group_vertices(
+                    p.flat.data_ptr(), p.counts.data_ptr(), off.data_ptr(), off2.data_ptr(), dt, B, H, W, V, K,
+                    c.score.data_ptr(), c.xy.data_ptr(), Cv, dec.down_sample, g.kpt_proj.data_ptr(), g.kpt_score.data_ptr(),
+                    g.kpt_j.data_ptr(), g.verts.data_ptr(), stream), "rtm3d_group_vertices")
+                for name in ("kpt_proj", "kpt_score", "kpt_j", "verts"):
+                    getattr(gh, name).copy_(getattr(g, name), non_blocking=True)
+            if sync:
+                torch.cuda.current_stream(self.dev).synchronize()
+        return self.det_host, self.grp_host
 
 
 def decoder_from_config(config) -> HeatmapDecoder:
