@@ -46,8 +46,10 @@ enum rtm3d_error {
 };
 
 /* rtm3d_decode_main flags */
-#define RTM3D_FLAG_FORCE_GENERIC 1u /* use the shape-generic strip kernels even when the streaming kernel applies */
-#define RTM3D_FLAG_CLUSTER(s) (((unsigned)(s) & 0xFu) << 8) /* streaming kernel: force s CTAs (1,2,4,8) per image; 0 = auto */
+#define RTM3D_FLAG_FORCE_GENERIC 1u /* use the shape-generic strip kernels even when the plane-streaming kernel applies */
+#define RTM3D_FLAG_NO_SPECULATION 2u /* plane-streaming kernel: never start a plane at the previous plane's threshold */
+#define RTM3D_FLAG_MAX_CTAS(n) (((unsigned)(n) & 0xFFu) << 16) /* plane-streaming kernel: at most n CTAs (0 = one per SM) */
+#define RTM3D_FLAG_SPLIT(s) (((unsigned)(s) & 0xFu) << 8) /* plane-streaming kernel: force s strips (1,2,4,8) per plane; 0 = auto */
 
 int rtm3d_abi_version(void);
 const char* rtm3d_last_error(void);
@@ -150,6 +152,21 @@ int rtm3d_decode_box3d(const int32_t* flat, const int32_t* counts, const void* r
                        int B, int C, int H, int W, int Creg, int K, int mode,
                        const float* cam, const float* dim_ref, float depth_mu, float depth_sigma,
                        float* loc, float* dim, float* alpha, float* rot_y, float* corners2d, void* stream);
+
+/*
+ * The library's sigmoid s(x) = 1.0f / (1.0f + expf(-x)) applied element-wise to n device floats: the function every
+ * score of this library goes through (models/model.py:48,85,107 `sigmoid_`).  Exposed so that tests can sweep all 2^32
+ * inputs: bit-identical to torch's CUDA sigmoid, and monotone (the peak test relies on it).
+ */
+int rtm3d_sigmoid_f32(const float* x, float* y, size_t n, void* stream);
+
+/*
+ * Verification aid for the plane-streaming kernel's running threshold: for every bin b of its score histogram,
+ * score_edge_bits[b] = fp32 bits of the bin's lower score edge and logit_bound[b] = the logit T the scan uses for it,
+ * with the contract  x < T  =>  rtm3d_sigmoid_f32(x) < edge  (bin 0: no bound, T = -inf).  *n_bins is always set; the
+ * device arrays (capacity >= *n_bins entries) may both be NULL to query the size only.
+ */
+int rtm3d_threshold_table(float* logit_bound, uint32_t* score_edge_bits, int capacity, int* n_bins, void* stream);
 
 #ifdef __cplusplus
 }

@@ -62,11 +62,24 @@ void carve(rtm3d::DecodeParams& p, const rtm3d::WorkspaceLayout& L, void* ws) {
 
 int dispatch(rtm3d::DecodeParams& p, const rtm3d::WorkspaceLayout& L, int dtype, int mode, unsigned flags,
              cudaStream_t s) {
-  p.cluster_override = static_cast<int>((flags >> 8) & 0xFu);
-  p.debug = static_cast<int>((flags >> 16) & 0xFu);
   if (!(flags & RTM3D_FLAG_FORCE_GENERIC)) {
-    const int rc = rtm3d::launch_stream(p, dtype, mode, s);   // -1000: shape (or forced cluster size) not eligible
-    if (rc != -1000) return cuda_fail(rc, "decode (streaming kernel) launch");
+    rtm3d::PlaneParams q{};
+    const bool main = mode == rtm3d::kModeMain;
+    q.hm_main = main ? p.hm : nullptr;
+    q.hm_kpt = main ? nullptr : p.hm;
+    q.off = p.off;
+    q.off2_main = main ? p.off2 : nullptr;
+    q.off2_kpt = main ? nullptr : p.off2;
+    q.B = p.B; q.C = main ? p.C : 0; q.Cv = main ? 0 : p.C; q.H = p.H; q.W = p.W; q.n_vert = p.n_vert; q.K = p.K;
+    q.thresh = p.thresh; q.down = p.down; q.t0 = p.t0;
+    q.cls = p.cls; q.score = p.score; q.proj = p.proj; q.verts = p.verts; q.bbox = p.bbox; q.flat = p.flat; q.counts = p.counts;
+    q.kscore = p.kscore; q.kxy = p.kxy; q.kflat = p.kflat;
+    q.tickets = p.tickets; q.keys = p.keys; q.key_counts = p.key_counts; q.status = p.status;
+    q.retry = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(p.tickets) - L.tickets_off + L.retry_off);
+    q.guess = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(p.tickets) - L.tickets_off + L.guess_off);
+    const int rc = rtm3d::launch_planes(q, dtype, static_cast<int>((flags >> 8) & 0xFu), (flags & RTM3D_FLAG_NO_SPECULATION) ? 0 : 1,
+                                        static_cast<int>((flags >> 16) & 0xFFu), static_cast<int>((flags >> 24) & 0xFu), s);   // -1000: shape not eligible
+    if (rc != -1000) return cuda_fail(rc, "decode (plane-streaming kernel) launch");
   }
   if (L.generic_smem > 200 * 1024) return fail(RTM3D_ERR_SHAPE, "row too wide for the generic kernel (%zu B smem)", L.generic_smem);
   return cuda_fail(rtm3d::launch_generic(p, dtype, mode, L.generic_smem, s), "decode (generic kernel) launch");
@@ -85,12 +98,12 @@ const char* rtm3d_build_info(void) {
 #define RTM3D_STR2(x) #x
 #define RTM3D_STR(x) RTM3D_STR2(x)
       RTM3D_STR(__CUDACC_VER_MAJOR__) "." RTM3D_STR(__CUDACC_VER_MINOR__)
-      " sm_100a; kernels: decode_stream (cp.async.bulk ring + selector warp), decode_generic (strip/merge),"
+      " sm_100a; kernels: decode_planes (persistent, cp.async.bulk ring, histogram select), decode_generic (strip/merge),"
       " group_vertices, box3d; fp32+bf16 inputs";
 }
 
-/* developer instrumentation (tools/timeline.py); deliberately absent from include/rtm3d_decode.h */
-void rtm3d_debug_set_timeline(void* dev_u64_16_per_cta) { rtm3d::debug_set_timeline(static_cast<unsigned long long*>(dev_u64_16_per_cta)); }
+/* developer instrumentation (tools/plane_stats.py); deliberately absent from include/rtm3d_decode.h */
+void rtm3d_debug_set_stats(void* dev_u64_16) { rtm3d::debug_set_stats(static_cast<unsigned long long*>(dev_u64_16)); }
 
 int rtm3d_decode_workspace_bytes(int B, int C, int H, int W, int K, size_t* out_bytes) {
   if (!out_bytes) return fail(RTM3D_ERR_NULL, "out_bytes is NULL");
@@ -238,6 +251,20 @@ int rtm3d_decode_box3d(const int32_t* flat, const int32_t* counts, const void* r
   if (Creg != (multibin ? 14 : 8)) return fail(RTM3D_ERR_SHAPE, "Creg=%d does not match mode %d (8 SMOKE-style, 14 multi-bin)", Creg, mode);
   rtm3d::Box3dParams q{flat, counts, reg, B, C, H, W, Creg, K, mode, cam, dim_ref, depth_mu, depth_sigma, loc, dim, alpha, rot_y, corners2d};
   return cuda_fail(rtm3d::launch_box3d(q, dtype, static_cast<cudaStream_t>(stream)), "box3d launch");
+}
+
+int rtm3d_sigmoid_f32(const float* x, float* y, size_t n, void* stream) {
+  if (!x || !y) return fail(RTM3D_ERR_NULL, "NULL pointer argument");
+  return cuda_fail(rtm3d::launch_sigmoid(x, y, n, static_cast<cudaStream_t>(stream)), "sigmoid launch");
+}
+
+int rtm3d_threshold_table(float* logit_bound, uint32_t* score_edge_bits, int capacity, int* n_bins, void* stream) {
+  if (!n_bins) return fail(RTM3D_ERR_NULL, "n_bins is NULL");
+  *n_bins = rtm3d::threshold_table_bins();
+  if (!logit_bound && !score_edge_bits) return 0;
+  if (!logit_bound || !score_edge_bits) return fail(RTM3D_ERR_NULL, "NULL pointer argument");
+  if (capacity < *n_bins) return fail(RTM3D_ERR_WORKSPACE, "capacity %d < %d bins", capacity, *n_bins);
+  return cuda_fail(rtm3d::launch_threshold_table(logit_bound, score_edge_bits, static_cast<cudaStream_t>(stream)), "threshold table launch");
 }
 
 }  // extern "C"

@@ -141,14 +141,22 @@ WorkspaceLayout workspace_layout(int B, int C, int H, int W, int K) {
   L.generic_smem = generic_smem_bytes(W, K, L.strip_rows, L.list_cap);
   size_t off = 0;
   L.tickets_off = off;
-  off += ((static_cast<size_t>(B) * C * 4 + 255) / 256) * 256;
+  off += ((static_cast<size_t>(B) * (C + 1) * 4 + 255) / 256) * 256;
   L.status_off = off;
   off += 256;
   L.keys_off = off;
-  off += static_cast<size_t>(B) * C * L.nstrips * K * 8;
+  // units: strips of the generic kernel, or items (<= kPlanesMaxSplit strips per plane) of the plane-streaming kernel
+  const size_t units = static_cast<size_t>(B) * C * (L.nstrips > kPlanesMaxSplit ? L.nstrips : kPlanesMaxSplit);
+  off += units * K * 8;
   off = (off + 255) / 256 * 256;
   L.counts_off = off;
-  off += static_cast<size_t>(B) * C * L.nstrips * 4;
+  off += units * 4;
+  off = (off + 255) / 256 * 256;
+  L.retry_off = off;
+  off += units * 4;
+  off = (off + 255) / 256 * 256;
+  L.guess_off = off;
+  off += 256;
   L.total = (off + 255) / 256 * 256;
   return L;
 }

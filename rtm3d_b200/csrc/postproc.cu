@@ -162,6 +162,16 @@ __global__ void __launch_bounds__(128) box3d_kernel(const Box3dParams p) {
   for (int i = 0; i < 16; ++i) p.corners2d[row * 16 + i] = uv[i];
 }
 
+// The library's sigmoid, element-wise (verification aid: tests sweep every fp32 value through it).
+__global__ void sigmoid_kernel(const float* x, float* y, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    y[i] = sigmoid_ref(x[i]);
+}
+int launch_sigmoid(const float* x, float* y, size_t n, cudaStream_t s) {
+  sigmoid_kernel<<<148 * 8, 256, 0, s>>>(x, y, n);
+  return static_cast<int>(cudaGetLastError());
+}
+
 int launch_box3d(const Box3dParams& p, int dtype, cudaStream_t s) {
   dim3 grid((p.K + 127) / 128, p.B);
   if (dtype == 0) box3d_kernel<float><<<grid, 128, 0, s>>>(p);

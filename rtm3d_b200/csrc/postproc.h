@@ -23,5 +23,6 @@ struct Box3dParams {
 
 int launch_group(const GroupParams& p, int dtype, cudaStream_t s);
 int launch_box3d(const Box3dParams& p, int dtype, cudaStream_t s);
+int launch_sigmoid(const float* x, float* y, size_t n, cudaStream_t s);
 
 }  // namespace rtm3d

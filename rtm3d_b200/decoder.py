@@ -94,7 +94,7 @@ class HeatmapDecoder:
     (DETECTOR.SCORE_THRESH, DETECTOR.TOPK_CANDIDATES, MODEL.DOWN_SAMPLE -- models/model.py:41-42,67,70)."""
 
     def __init__(self, score_thresh: float = 0.5, topk: int = 30, down_sample: float = 4.0, force_generic: bool = False,
-                 cluster: int = 0):
+                 split: int = 0, speculate: bool = True, max_ctas: int = 0):
         if not (score_thresh >= 0):
             raise ValueError("score_thresh must be >= 0: zero-score fillers of the peak map could pass a negative threshold")
         if not (1 <= int(topk) <= 1024):
@@ -102,9 +102,12 @@ class HeatmapDecoder:
         self.score_thresh = float(score_thresh)
         self.topk = int(topk)
         self.down_sample = float(down_sample)
-        if cluster not in (0, 1, 2, 4, 8):
-            raise ValueError("cluster (CTAs per image of the streaming kernel) must be 0 (auto), 1, 2, 4 or 8")
-        self.flags = (_native.FLAG_FORCE_GENERIC if force_generic else 0) | (cluster << 8)
+        if split not in (0, 1, 2, 4, 8):
+            raise ValueError("split (strips per plane of the plane-streaming kernel) must be 0 (auto), 1, 2, 4 or 8")
+        if not (0 <= int(max_ctas) <= 255):
+            raise ValueError("max_ctas must be in [0, 255] (0 = one CTA per SM)")
+        self.flags = ((_native.FLAG_FORCE_GENERIC if force_generic else 0) | (0 if speculate else _native.FLAG_NO_SPECULATION)
+                      | (split << 8) | (int(max_ctas) << 16))
         self._lib = _native.lib()
         self._ws = {}
 

@@ -17,10 +17,10 @@ from rtm3d_b200 import HeatmapDecoder, synth
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 FLOAT_FIELDS = ("score", "proj", "verts", "bbox")
-# kernel variants: the shape-generic strip kernels, the streaming kernel with its own choice of cluster size (falls
-# back to generic on ineligible shapes), and the streaming kernel forced to 1/2/4/8 CTAs per image
-VARIANTS = [dict(force_generic=True), dict(), dict(cluster=1), dict(cluster=2), dict(cluster=4), dict(cluster=8)]
-VARIANT_IDS = ["generic", "auto", "c1", "c2", "c4", "c8"]
+# kernel variants: the shape-generic strip kernels, the plane-streaming kernel with its own choice of strips per plane
+# (falls back to generic on ineligible shapes), and the plane-streaming kernel forced to 1/2/4/8 strips per plane
+VARIANTS = [dict(force_generic=True), dict(), dict(split=1), dict(split=2), dict(split=4), dict(split=8)]
+VARIANT_IDS = ["generic", "auto", "s1", "s2", "s4", "s8"]
 
 
 def _rows(packed, b):
@@ -190,3 +190,37 @@ def test_repeatable_and_workspace_self_cleaning():
         again = dec.decode_packed(dev)
         for f in ("cls", "score", "proj", "verts", "bbox", "flat", "counts"):
             assert torch.equal(getattr(first, f), getattr(again, f)), f
+
+
+@pytest.mark.parametrize("max_ctas", [1, 3, 0])
+@pytest.mark.parametrize("speculate", [True, False])
+def test_speculative_start_threshold_is_exact(max_ctas, speculate):
+    """The plane-streaming kernel starts a plane at the threshold remembered from the previous plane of the same index
+    (a few bins lower) and redoes the plane when that turns out too high.  Batches whose images alternate between
+    strong, weak, empty and plateau maps make the guess fail constantly; few CTAs make every CTA see many planes."""
+    B, C, H, W, K = 24, 3, 48, 80, 50
+    logits, kpt = synth.head_outputs(B, C, H, W, seed=4242, kind="randn", kpt_channels=9)
+    scale = torch.tensor([3.0, 0.05, 1.0, 0.3, 6.0, 0.0])[torch.arange(B) % 6].view(B, 1, 1, 1)
+    shift = torch.tensor([0.0, -3.0, 2.0, 0.0, -8.0, 1.0])[torch.arange(B) % 6].view(B, 1, 1, 1)
+    logits[0] = logits[0] * scale + shift
+    kpt = kpt * scale + shift
+    dev_logits = [t.to(DEV) for t in logits]
+    dec = HeatmapDecoder(0.4, K, 4.0, speculate=speculate, max_ctas=max_ctas)
+    packed = dec.decode_packed(dev_logits)
+    cand = dec.decode_keypoints(kpt.to(DEV), dev_logits[3])
+    torch.cuda.synchronize()
+    for b in range(B):
+        r = decode_ref.decode_image(dev_logits[0][b], dev_logits[1][b], dev_logits[2][b], 0.4, K, 4.0)
+        got = _rows(packed, b)
+        if r is None:
+            assert len(got["flat"]) == 0
+        else:
+            parity.assert_exact(got, _oracle_rows(r), ("flat", "cls", "score", "proj", "verts", "bbox"), f"image {b}")
+        vs, vx, vy, vflat = decode_ref.keypoint_peaks(kpt[b].to(DEV), K)
+        for c in range(9):
+            o = np.lexsort((vflat[c].cpu().numpy(), -vs[c].cpu().numpy().astype(np.float64)))
+            assert np.array_equal(cand.flat[b, c].cpu().numpy(), vflat[c].cpu().numpy()[o]), f"b{b} c{c} kflat"
+            assert np.array_equal(cand.score[b, c].cpu().numpy().view(np.uint32), vs[c].cpu().numpy()[o].view(np.uint32))
+    # the workspace is left clean: a second run gives the same result
+    again = dec.decode_packed(dev_logits)
+    assert torch.equal(again.flat, packed.flat) and torch.equal(again.score, packed.score)

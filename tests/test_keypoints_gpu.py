@@ -11,8 +11,8 @@ from rtm3d_b200 import HeatmapDecoder, synth
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-VARIANTS = [dict(force_generic=True), dict(), dict(cluster=1), dict(cluster=2), dict(cluster=4)]
-VARIANT_IDS = ["generic", "auto", "c1", "c2", "c4"]
+VARIANTS = [dict(force_generic=True), dict(), dict(split=1), dict(split=2), dict(split=4)]
+VARIANT_IDS = ["generic", "auto", "s1", "s2", "s4"]
 
 
 def _check(logits_cpu, kpt_cpu, K, variant, what):

@@ -15,7 +15,7 @@ def run(name, generic, nsets=4, iters=20, kind="randn"):
         hm = mk(C)
         if kind == "trained": hm = hm * 3 - 6
         sets.append([hm, mk(16), mk(2), mk(2)])
-    dec = HeatmapDecoder(0.4, K, 4.0, force_generic=True) if generic is True else HeatmapDecoder(0.4, K, 4.0, cluster=int(generic))
+    dec = HeatmapDecoder(0.4, K, 4.0, force_generic=True) if generic is True else HeatmapDecoder(0.4, K, 4.0, split=int(generic))
     for s in sets: dec.decode_packed(s)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
