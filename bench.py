@@ -195,7 +195,7 @@ def run_b200(args, w):
     nsets = 2
     sets = [make_inputs(torch, w, dev, 1234 + rank + 100 * s) for s in range(nsets)]
     heat_bytes = B * (w["C"] + Cv) * w["H"] * w["W"] * 4
-    launches_per_step = 3 if Cv else 1
+    launches_per_step = 2 if Cv else 1      # fused plane-streaming kernel (+ grouping kernel)
 
     gather_out = None
 
@@ -250,7 +250,7 @@ def run_b200(args, w):
 
     # per-kernel durations from the marks (each step: before, after main, [after kpt, after group])
     per = launches_per_step + 1
-    names = ["decode_main", "decode_keypoints", "group_vertices"][:launches_per_step]
+    names = ["decode_planes(main+kpt)", "group_vertices"] if Cv else ["decode_planes(main)"]
     kernel_ms = {n: 0.0 for n in names}
     for s in range(args.steps):
         for j, n in enumerate(names):
@@ -281,7 +281,7 @@ def run_b200(args, w):
         peak, peak_src = peaks()
         A, A_main, A_kpt = algorithmic_bytes_per_image(w)
         dom = max(kernel_ms, key=kernel_ms.get)
-        dom_bytes = B * (A_kpt if dom == "decode_keypoints" else A_main if dom == "decode_main" else 0)
+        dom_bytes = B * (A if dom.startswith("decode_planes(main+kpt)") else A_main if dom.startswith("decode_planes") else 0)
         achieved = dom_bytes / (kernel_ms[dom] * 1e-3) / 1e9 if kernel_ms[dom] > 0 else 0.0
         step_gbs = B * A / (ms_step * 1e-3) / 1e9
         line = {

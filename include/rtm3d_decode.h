@@ -48,6 +48,7 @@ enum rtm3d_error {
 /* rtm3d_decode_main flags */
 #define RTM3D_FLAG_FORCE_GENERIC 1u /* use the shape-generic strip kernels even when the plane-streaming kernel applies */
 #define RTM3D_FLAG_NO_SPECULATION 2u /* plane-streaming kernel: never start a plane at the previous plane's threshold */
+#define RTM3D_FLAG_NO_GROUP 4u /* rtm3d_decode_fused: stop after the two decodes (the caller runs rtm3d_group_vertices itself) */
 #define RTM3D_FLAG_MAX_CTAS(n) (((unsigned)(n) & 0xFFu) << 16) /* plane-streaming kernel: at most n CTAs (0 = one per SM) */
 #define RTM3D_FLAG_SPLIT(s) (((unsigned)(s) & 0xFu) << 8) /* plane-streaming kernel: force s strips (1,2,4,8) per plane; 0 = auto */
 
@@ -123,6 +124,20 @@ int rtm3d_decode_keypoints_host(const void* kpt_hm_host, const void* voff2_host,
                                 float* kscore, float* kxy, int32_t* kflat,
                                 float* kscore_host, float* kxy_host, int32_t* kflat_host,
                                 void* ws, size_t ws_bytes, unsigned flags, void* stream);
+
+/*
+ * Tier A + Tier B in ONE enqueue -- the full Model.inference with the commented keypoint wiring restored
+ * (models/model.py:45-62, 68-69): rtm3d_decode_main on (hm, off, off2), rtm3d_decode_keypoints on (kpt_hm, voff2) and
+ * rtm3d_group_vertices on their results.  Both heat-maps are streamed by a single launch of the plane-streaming
+ * kernel (C + Cv planes per image share the GPU), followed by the grouping kernel.  Arguments as in the three entry
+ * points; the workspace must be sized with rtm3d_decode_workspace_bytes(B, C + Cv, H, W, K).
+ */
+int rtm3d_decode_fused(const void* hm, const void* off, const void* off2, const void* kpt_hm, const void* voff2, int dtype,
+                       int B, int C, int Cv, int H, int W, int n_vert, int K, float thresh, float down,
+                       int64_t* cls, float* score, float* proj, float* verts, float* bbox, int32_t* flat, int32_t* counts,
+                       float* kscore, float* kxy, int32_t* kflat,
+                       float* kpt_proj, float* kpt_score, int32_t* kpt_j, float* verts_cv,
+                       void* ws, size_t ws_bytes, unsigned flags, void* stream);
 
 /*
  * Tier B -- _group_vertexs_kf (models/model.py:134-162): for every detection n of rtm3d_decode_main and keypoint

@@ -226,6 +226,60 @@ int rtm3d_decode_keypoints_host(const void* kpt_hm_host, const void* voff2_host,
   return 0;
 }
 
+int rtm3d_decode_fused(const void* hm, const void* off, const void* off2, const void* kpt_hm, const void* voff2, int dtype,
+                       int B, int C, int Cv, int H, int W, int n_vert, int K, float thresh, float down, int64_t* cls,
+                       float* score, float* proj, float* verts, float* bbox, int32_t* flat, int32_t* counts, float* kscore,
+                       float* kxy, int32_t* kflat, float* kpt_proj, float* kpt_score, int32_t* kpt_j, float* verts_cv,
+                       void* ws, size_t ws_bytes, unsigned flags, void* stream) {
+  if (!hm || !off || !off2 || !kpt_hm || !voff2 || !cls || !score || !proj || !verts || !bbox || !flat || !counts || !kscore ||
+      !kxy || !kflat || !kpt_proj || !kpt_score || !kpt_j || !ws)
+    return fail(RTM3D_ERR_NULL, "NULL pointer argument");
+  if (dtype != RTM3D_F32 && dtype != RTM3D_BF16) return fail(RTM3D_ERR_DTYPE, "dtype %d", dtype);
+  if (Cv < 1) return fail(RTM3D_ERR_SHAPE, "Cv=%d", Cv);
+  if (int e = check_shape(B, C, H, W, K)) return e;
+  if (int e = check_shape(B, C + Cv, H, W, K)) return e;
+  if (n_vert < 1 || n_vert > RTM3D_MAX_VERTS) return fail(RTM3D_ERR_SHAPE, "n_vert=%d outside [1,%d]", n_vert, RTM3D_MAX_VERTS);
+  if (static_cast<long long>(K) > static_cast<long long>(H) * W) return fail(RTM3D_ERR_TOPK, "K=%d > H*W", K);
+  if (!(thresh >= 0.0f)) return fail(RTM3D_ERR_THRESH, "score threshold must be >= 0 (got %g)", thresh);
+  const rtm3d::WorkspaceLayout L = rtm3d::workspace_layout(B, C + Cv, H, W, K);
+  if (ws_bytes < L.total) return fail(RTM3D_ERR_WORKSPACE, "workspace %zu B < required %zu B", ws_bytes, L.total);
+  if (reinterpret_cast<uintptr_t>(ws) % 256) return fail(RTM3D_ERR_ALIGN, "workspace must be 256-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  bool fused = false;
+  if (!(flags & RTM3D_FLAG_FORCE_GENERIC)) {
+    unsigned char* base = static_cast<unsigned char*>(ws);
+    rtm3d::PlaneParams q{};
+    q.hm_main = hm; q.hm_kpt = kpt_hm; q.off = off; q.off2_main = off2; q.off2_kpt = voff2;
+    q.B = B; q.C = C; q.Cv = Cv; q.H = H; q.W = W; q.n_vert = n_vert; q.K = K;
+    q.thresh = thresh; q.down = down; q.t0 = prefilter_logit(thresh);
+    q.cls = cls; q.score = score; q.proj = proj; q.verts = verts; q.bbox = bbox; q.flat = flat; q.counts = counts;
+    q.kscore = kscore; q.kxy = kxy; q.kflat = kflat;
+    q.tickets = reinterpret_cast<uint32_t*>(base + L.tickets_off);
+    q.keys = reinterpret_cast<uint64_t*>(base + L.keys_off);
+    q.key_counts = reinterpret_cast<uint32_t*>(base + L.counts_off);
+    q.status = reinterpret_cast<uint32_t*>(base + L.status_off);
+    q.retry = reinterpret_cast<uint32_t*>(base + L.retry_off);
+    q.guess = reinterpret_cast<uint32_t*>(base + L.guess_off);
+    const int rc = rtm3d::launch_planes(q, dtype, static_cast<int>((flags >> 8) & 0xFu), (flags & RTM3D_FLAG_NO_SPECULATION) ? 0 : 1,
+                                        static_cast<int>((flags >> 16) & 0xFFu), static_cast<int>((flags >> 24) & 0xFu), s);
+    if (rc != -1000) {
+      if (int e = cuda_fail(rc, "decode (plane-streaming kernel, fused) launch")) return e;
+      fused = true;
+    }
+  }
+  if (!fused) {
+    // shapes the plane-streaming kernel does not take: the two separate entry points (generic kernels) on one workspace
+    if (int e = rtm3d_decode_main(hm, off, off2, dtype, B, C, H, W, n_vert, K, thresh, down, cls, score, proj, verts, bbox, flat,
+                                  counts, ws, ws_bytes, flags, stream))
+      return e;
+    if (int e = rtm3d_decode_keypoints(kpt_hm, voff2, dtype, B, Cv, H, W, K, kscore, kxy, kflat, ws, ws_bytes, flags, stream))
+      return e;
+  }
+  if (flags & RTM3D_FLAG_NO_GROUP) return 0;
+  return rtm3d_group_vertices(flat, counts, off, off2, dtype, B, H, W, n_vert, K, kscore, kxy, Cv, down, kpt_proj, kpt_score,
+                              kpt_j, verts_cv, stream);
+}
+
 int rtm3d_group_vertices(const int32_t* flat, const int32_t* counts, const void* off, const void* off2, int dtype, int B,
                          int H, int W, int n_vert, int K, const float* kscore, const float* kxy, int Cv, float down,
                          float* kpt_proj, float* kpt_score, int32_t* kpt_j, float* verts_cv, void* stream) {

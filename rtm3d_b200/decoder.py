@@ -219,23 +219,69 @@ class HeatmapDecoder:
         _native.check(rc, "rtm3d_group_vertices")
         return out
 
-    def decode_with_keypoints(self, pred_logits, kpt_logits, marks=None):
+    def decode_with_keypoints(self, pred_logits, kpt_logits, marks=None, fused=True):
         """Tier A + Tier B as the commented wiring of models/model.py:45-62,68-69 describes.  Returns
-        (PackedDetections, KeypointCandidates, GroupedKeypoints), all asynchronous.  ``marks``: optional list that
-        receives a recorded ``torch.cuda.Event`` before the first and after each of the three launches (bench.py times
-        the individual kernels with it)."""
+        (PackedDetections, KeypointCandidates, GroupedKeypoints), all asynchronous.  ``fused`` (default): one call of
+        ``rtm3d_decode_fused`` -- both heat-maps streamed by a single kernel launch, then the grouping kernel; otherwise
+        the three separate entry points.  ``marks``: optional list that receives a recorded ``torch.cuda.Event`` before
+        the first and after every kernel (bench.py times the kernels with it; the fused call is then issued as
+        decode-without-grouping + ``rtm3d_group_vertices``, the same two launches with an event in between)."""
         def mark():
             if marks is not None:
                 e = torch.cuda.Event(enable_timing=True)
                 e.record()
                 marks.append(e)
-        mark()
-        det = self.decode_packed(pred_logits)
-        mark()
-        cand = self.decode_keypoints(kpt_logits, pred_logits[3])
-        mark()
-        grp = self.group_keypoints(det, cand, pred_logits)
-        mark()
+        if not fused:
+            mark()
+            det = self.decode_packed(pred_logits)
+            mark()
+            cand = self.decode_keypoints(kpt_logits, pred_logits[3])
+            mark()
+            grp = self.group_keypoints(det, cand, pred_logits)
+            mark()
+            return det, cand, grp
+        main, off, off2, voff2 = pred_logits[0], pred_logits[1], pred_logits[2], pred_logits[3]
+        _check_map(main, "main_kf")
+        B, C, H, W = main.shape
+        if off.shape[1] % 2:
+            raise ValueError("offset_fr_main must have an even channel count (dx,dy per vertex)")
+        V = off.shape[1] // 2
+        _check_map(off, "offset_fr_main", (B, 2 * V, H, W))
+        _check_map(off2, "main_offset", (B, 2, H, W))
+        _check_map(voff2, "vertex_offset", (B, 2, H, W))
+        _check_map(kpt_logits, "vertex_kf")
+        Cv = kpt_logits.shape[1]
+        if tuple(kpt_logits.shape) != (B, Cv, H, W):
+            raise ValueError("vertex_kf must have the main heat-map's batch and spatial shape")
+        maps = (main, off, off2, voff2, kpt_logits)
+        if len({t.dtype for t in maps}) != 1 or len({t.device for t in maps}) != 1:
+            raise ValueError("head maps must share dtype and device")
+        dt, dev, K = _dtype_code(main), main.device, self.topk
+        e = lambda *sh, d=torch.float32: torch.empty(sh, dtype=d, device=dev)
+        with torch.cuda.device(dev):
+            ws, stream = self._workspace(dev, B, C + Cv, H, W)
+            det = PackedDetections(cls=e(B, K, d=torch.int64), score=e(B, K), proj=e(B, K, 2), verts=e(B, K, V, 2),
+                                   bbox=e(B, K, 4), flat=e(B, K, d=torch.int32), counts=e(B, d=torch.int32))
+            cand = KeypointCandidates(score=e(B, Cv, K), xy=e(B, Cv, K, 2), flat=e(B, Cv, K, d=torch.int32))
+            grp = GroupedKeypoints(kpt_proj=e(B, K, Cv, 2), kpt_score=e(B, K, Cv), kpt_j=e(B, K, Cv, d=torch.int32),
+                                   verts=e(B, K, Cv, 2))
+            mark()
+            rc = self._lib.rtm3d_decode_fused(
+                main.data_ptr(), off.data_ptr(), off2.data_ptr(), kpt_logits.data_ptr(), voff2.data_ptr(), dt,
+                B, C, Cv, H, W, V, K, self.score_thresh, self.down_sample,
+                det.cls.data_ptr(), det.score.data_ptr(), det.proj.data_ptr(), det.verts.data_ptr(), det.bbox.data_ptr(),
+                det.flat.data_ptr(), det.counts.data_ptr(), cand.score.data_ptr(), cand.xy.data_ptr(), cand.flat.data_ptr(),
+                grp.kpt_proj.data_ptr(), grp.kpt_score.data_ptr(), grp.kpt_j.data_ptr(), grp.verts.data_ptr(),
+                ws.data_ptr(), ws.numel(), self.flags | (_native.FLAG_NO_GROUP if marks is not None else 0), stream)
+            mark()
+            _native.check(rc, "rtm3d_decode_fused")
+            if marks is not None:
+                rc = self._lib.rtm3d_group_vertices(
+                    det.flat.data_ptr(), det.counts.data_ptr(), off.data_ptr(), off2.data_ptr(), dt, B, H, W, V, K,
+                    cand.score.data_ptr(), cand.xy.data_ptr(), Cv, self.down_sample, grp.kpt_proj.data_ptr(),
+                    grp.kpt_score.data_ptr(), grp.kpt_j.data_ptr(), grp.verts.data_ptr(), stream)
+                mark()
+                _native.check(rc, "rtm3d_group_vertices")
         return det, cand, grp
 
     # ------------------------------------------------------------------ Tier C

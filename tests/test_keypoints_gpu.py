@@ -11,15 +11,18 @@ from rtm3d_b200 import HeatmapDecoder, synth
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-VARIANTS = [dict(force_generic=True), dict(), dict(split=1), dict(split=2), dict(split=4)]
-VARIANT_IDS = ["generic", "auto", "s1", "s2", "s4"]
+# fused: both heat-maps in one launch of the plane-streaming kernel (rtm3d_decode_fused); separate: the three entry points
+VARIANTS = [dict(force_generic=True), dict(), dict(split=1), dict(split=2), dict(split=4), dict(fused=False), dict(fused=False, split=2)]
+VARIANT_IDS = ["generic", "auto", "s1", "s2", "s4", "separate", "separate-s2"]
 
 
 def _check(logits_cpu, kpt_cpu, K, variant, what):
     logits = [t.to(DEV) for t in logits_cpu]
     kpt = kpt_cpu.to(DEV)
+    variant = dict(variant)
+    fused = variant.pop("fused", True)
     dec = HeatmapDecoder(0.4, K, 4.0, **variant)
-    det, cand, grp = dec.decode_with_keypoints(logits, kpt)
+    det, cand, grp = dec.decode_with_keypoints(logits, kpt, fused=fused)
     torch.cuda.synchronize()
     B, Cv = kpt.shape[:2]
     for b in range(B):
