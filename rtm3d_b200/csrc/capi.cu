@@ -60,6 +60,19 @@ void carve(rtm3d::DecodeParams& p, const rtm3d::WorkspaceLayout& L, void* ws) {
   p.list_cap = L.list_cap;
 }
 
+// The wide epilogue kernels that follow the plane-streaming kernel (it writes score / flat / counts and kscore / kflat).
+int launch_epilogues(const rtm3d::PlaneParams& q, int dtype, cudaStream_t s) {
+  if (q.C > 0) {
+    rtm3d::EpiMainParams e{q.flat, q.counts, q.off, q.off2_main, q.B, q.C, q.H, q.W, q.n_vert, q.K, q.down, q.cls, q.proj, q.verts, q.bbox};
+    if (int r = cuda_fail(rtm3d::launch_epilogue_main(e, dtype, s), "Tier A epilogue launch")) return r;
+  }
+  if (q.Cv > 0) {
+    rtm3d::EpiKptParams e{q.kflat, q.off2_kpt, q.B, q.Cv, q.H, q.W, q.K, q.kxy};
+    if (int r = cuda_fail(rtm3d::launch_epilogue_kpt(e, dtype, s), "Tier B epilogue launch")) return r;
+  }
+  return 0;
+}
+
 int dispatch(rtm3d::DecodeParams& p, const rtm3d::WorkspaceLayout& L, int dtype, int mode, unsigned flags,
              cudaStream_t s) {
   if (!(flags & RTM3D_FLAG_FORCE_GENERIC)) {
@@ -77,9 +90,14 @@ int dispatch(rtm3d::DecodeParams& p, const rtm3d::WorkspaceLayout& L, int dtype,
     q.tickets = p.tickets; q.keys = p.keys; q.key_counts = p.key_counts; q.status = p.status;
     q.retry = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(p.tickets) - L.tickets_off + L.retry_off);
     q.guess = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(p.tickets) - L.tickets_off + L.guess_off);
+    if (main && !q.flat)   // the epilogue needs the flat indices even when the caller does not
+      q.flat = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(p.tickets) - L.tickets_off + L.flat_off);
     const int rc = rtm3d::launch_planes(q, dtype, static_cast<int>((flags >> 8) & 0xFu), (flags & RTM3D_FLAG_NO_SPECULATION) ? 0 : 1,
                                         static_cast<int>((flags >> 16) & 0xFFu), static_cast<int>((flags >> 24) & 0xFu), s);   // -1000: shape not eligible
-    if (rc != -1000) return cuda_fail(rc, "decode (plane-streaming kernel) launch");
+    if (rc != -1000) {
+      if (int e = cuda_fail(rc, "decode (plane-streaming kernel) launch")) return e;
+      return launch_epilogues(q, dtype, s);
+    }
   }
   if (L.generic_smem > 200 * 1024) return fail(RTM3D_ERR_SHAPE, "row too wide for the generic kernel (%zu B smem)", L.generic_smem);
   return cuda_fail(rtm3d::launch_generic(p, dtype, mode, L.generic_smem, s), "decode (generic kernel) launch");
@@ -264,6 +282,7 @@ int rtm3d_decode_fused(const void* hm, const void* off, const void* off2, const 
                                         static_cast<int>((flags >> 16) & 0xFFu), static_cast<int>((flags >> 24) & 0xFu), s);
     if (rc != -1000) {
       if (int e = cuda_fail(rc, "decode (plane-streaming kernel, fused) launch")) return e;
+      if (int e = launch_epilogues(q, dtype, s)) return e;
       fused = true;
     }
   }

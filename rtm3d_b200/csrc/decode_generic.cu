@@ -157,6 +157,8 @@ WorkspaceLayout workspace_layout(int B, int C, int H, int W, int K) {
   off = (off + 255) / 256 * 256;
   L.guess_off = off;
   off += 256;
+  L.flat_off = off;                                  // [B][K] flat peak indices when the caller does not ask for them
+  off += static_cast<size_t>(B) * K * 4;
   L.total = (off + 255) / 256 * 256;
   return L;
 }

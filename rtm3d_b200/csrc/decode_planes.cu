@@ -1,8 +1,8 @@
 // Persistent plane-streaming decode kernel for sm_100a.
 //
-// Work item = one strip (H/split rows) of one heat-map plane:
-//   main planes   (b, c < C)   -> selection problem "image b"      : flat top-K over C*H*W      (models/model.py:87-98)
-//   keypoint planes (b, c < Cv) -> selection problem "plane (b,c)"  : per-channel top-K over H*W (models/model.py:109-114)
+// Work item = one strip (H/split rows) of
+//   the C main planes of image b  -> selection problem "image b"      : flat top-K over C*H*W      (models/model.py:87-98)
+//   keypoint plane (b, c < Cv)    -> selection problem "plane (b,c)"  : per-channel top-K over H*W (models/model.py:109-114)
 // One CTA per SM walks the items blockIdx.x, blockIdx.x + gridDim.x, ...  Both heat-maps of a batch can be decoded by
 // ONE launch (hm_main and hm_kpt both set); the two public entry points use the same kernel with one of them absent.
 //
@@ -28,8 +28,9 @@
 //   finishers          take over an item once every scanner has left it (hist/list are double-buffered, the scanners go
 //                      straight on to the next item): cut the list at the final threshold, sort the survivors, then either
 //                      emit the rows (problem with one part) or publish the part's top-K and let the last part to arrive
-//                      merge and emit (gathers of the regression maps, sub-pixel add, vertex regress, 2D box:
-//                      models/model.py:47-50,63-73,117-132).
+//                      merge and write the selection (score, flat index).  The gathers of the regression maps, sub-pixel
+//                      add, vertex regress and 2D box (models/model.py:47-50,63-73,117-132) follow in two small, wide
+//                      epilogue kernels (postproc.cu).
 //
 // Adversarial inputs (plateaus, saturated or sorted maps) can produce more candidates than the list holds.  Then one
 // scanner warp takes the lock, waits until every handed-out slot is written, selects the exact K-th key (radix select),
@@ -178,15 +179,22 @@ struct __align__(16) PlaneCtl {
 };
 
 struct ItemInfo {
-  int b, plane, strip;          // plane < C: main plane, else keypoint plane (plane - C)
+  int b, slot, strip;           // slot 0 = the image's main planes (when C > 0), the following slots = keypoint planes
+  int plane;                    // index into the per-plane threshold memory: 0 for the main item, C + kc for keypoint plane kc
+  int kc;                       // keypoint plane (slot items), -1 for the main item
   bool is_main;
+  int nplanes;                  // planes streamed by this item: C for the main item (one flat top-K over C*H*W), else 1
   int ys, ye;                   // rows of the strip
-  int nchunks;
-  const unsigned char* base;    // plane base address
-  uint32_t flat_base;           // added to y*W+x to form the key's flat index
+  int cpp;                      // chunks per plane
+  int nchunks;                  // nplanes * cpp
+  const unsigned char* base;    // base address of the item's first plane
+  size_t plane_bytes;
+  uint32_t flat_base;           // added to y*W+x to form the key's flat index (first plane)
+  uint32_t hw;                  // H*W: flat_base advances by it from plane to plane
 };
 
-// The items of a CTA: blockIdx.x, blockIdx.x + gridDim.x, ...  (item = (b * planes + plane) * split + strip), walked
+// The items of a CTA: blockIdx.x, blockIdx.x + gridDim.x, ...  (item = (b * slots + slot) * split + strip; slot 0 = the image's main planes,
+// then one slot per keypoint plane), walked
 // without a division per item.
 struct ItemIter {
   int item, b, r;               // r = item - b * per_img
@@ -205,20 +213,21 @@ struct ItemIter {
 __device__ __forceinline__ ItemInfo decode_item(const PlaneParams& p, const PlaneGeom& g, const ItemIter& ii, int elem_bytes) {
   ItemInfo it;
   it.b = ii.b;
-  it.plane = ii.r >> g.split_shift;
+  it.slot = ii.r >> g.split_shift;
   it.strip = ii.r & (g.split - 1);
-  it.is_main = it.plane < p.C;
+  it.is_main = p.C > 0 && it.slot == 0;
+  it.kc = it.is_main ? -1 : it.slot - (p.C > 0 ? 1 : 0);
+  it.plane = it.is_main ? 0 : p.C + it.kc;
+  it.nplanes = it.is_main ? p.C : 1;
   it.ys = (it.strip * p.H) >> g.split_shift;
   it.ye = ((it.strip + 1) * p.H) >> g.split_shift;
-  it.nchunks = (it.ye - it.ys == g.rows_lo) ? g.nch_lo : g.nch_hi;
-  const size_t plane_bytes = static_cast<size_t>(p.H) * p.W * elem_bytes;
-  if (it.is_main) {
-    it.base = reinterpret_cast<const unsigned char*>(p.hm_main) + (static_cast<size_t>(it.b) * p.C + it.plane) * plane_bytes;
-    it.flat_base = static_cast<uint32_t>(it.plane) * static_cast<uint32_t>(p.H * p.W);
-  } else {
-    it.base = reinterpret_cast<const unsigned char*>(p.hm_kpt) + (static_cast<size_t>(it.b) * p.Cv + (it.plane - p.C)) * plane_bytes;
-    it.flat_base = 0u;
-  }
+  it.cpp = (it.ye - it.ys == g.rows_lo) ? g.nch_lo : g.nch_hi;
+  it.nchunks = it.nplanes * it.cpp;
+  it.hw = static_cast<uint32_t>(p.H * p.W);
+  it.plane_bytes = static_cast<size_t>(p.H) * p.W * elem_bytes;
+  it.flat_base = 0u;
+  if (it.is_main) it.base = reinterpret_cast<const unsigned char*>(p.hm_main) + static_cast<size_t>(it.b) * p.C * it.plane_bytes;
+  else it.base = reinterpret_cast<const unsigned char*>(p.hm_kpt) + (static_cast<size_t>(it.b) * p.Cv + it.kc) * it.plane_bytes;
   return it;
 }
 
@@ -495,96 +504,28 @@ __device__ __forceinline__ void warp_fin_sort(unsigned long long* a, int m, unsi
   __syncwarp();
 }
 
-// Tier A rows of image b from `cnt` sorted keys (models/model.py:47-50 gather + sub-pixel, :63-73 regress / scale / box),
-// 32 detections at a time: phase 1 gathers their 2V+2 regression scalars into shared memory (4 independent 4-byte reads in
-// flight per lane), phase 2 gives every lane one detection.  Rows >= cnt are zero-filled (cls = flat = -1).
-//   gbuf: shared scratch of this warp, >= 32 * (2V+2) floats, laid out [channel][lane]
-template <typename T>
-static __device__ __noinline__ void warp_emit_main(const PlaneParams& p, int b, const unsigned long long* sorted, int cnt,
-                                                   float* gbuf, int lane) {
-  const int V = p.n_vert, K = p.K, HW = p.H * p.W;
-  const int nch = 2 * V + 2;                      // channel 0,1: main_offset; 2 + c: offset_fr_main channel c
-  const T* off2 = reinterpret_cast<const T*>(p.off2_main) + static_cast<size_t>(b) * 2 * HW;
-  const T* off = reinterpret_cast<const T*>(p.off) + static_cast<size_t>(b) * 2 * V * HW;
+// Tier A selection of image b: score, flat index (and the count) of the `cnt` sorted keys; rows >= cnt get score 0 and
+// flat -1.  The gathers / regress / 2D box of models/model.py:47-50,63-73 run afterwards in epilogue_main_kernel, wide
+// over the batch, so that their scattered reads do not stall a streaming CTA.
+static __device__ __noinline__ void warp_write_main(const PlaneParams& p, int b, const unsigned long long* sorted, int cnt, int lane) {
+  const int K = p.K;
 #pragma unroll 1
-  for (int j0 = 0; j0 < K; j0 += 32) {
-    const int nrow = min(32, cnt - j0);           // detections of this block (may be <= 0)
-    // ---- phase 1: gathers, staged through registers so that all of a lane's reads are in flight before the first
-    // shared-memory store (a store to the generic `gbuf` pointer would otherwise fence every following load)
-    if (lane < nrow) {
-      const uint32_t rem = key_flat(sorted[j0 + lane]) % static_cast<uint32_t>(HW);
-      const T* s2 = off2 + rem;
-      const T* s16 = off + rem;
-      constexpr int kG = 18;
-#pragma unroll 1
-      for (int c0 = 0; c0 < nch; c0 += kG) {
-        float r[kG];
-#pragma unroll
-        for (int u = 0; u < kG; ++u) {
-          const int ch = c0 + u;
-          r[u] = 0.f;
-          if (ch < nch) r[u] = (ch < 2) ? to_f32(s2[static_cast<size_t>(ch) * HW]) : to_f32(s16[static_cast<size_t>(ch - 2) * HW]);
-        }
-#pragma unroll
-        for (int u = 0; u < kG; ++u)
-          if (c0 + u < nch) gbuf[(c0 + u) * 32 + lane] = r[u];
-      }
-    }
-    __syncwarp();
-    // ---- phase 2: one detection per lane
-    const int j = j0 + lane;
-    if (j < K) {
-      const size_t row = static_cast<size_t>(b) * K + j;
-      const bool valid = j < cnt;
-      float mx = 0.f, my = 0.f, lo_x = 0.f, lo_y = 0.f, hi_x = 0.f, hi_y = 0.f, sc = 0.f;
-      int c = -1, flat = -1;
-      if (valid) {
-        const unsigned long long key = sorted[j];
-        flat = static_cast<int>(key_flat(key));
-        sc = key_score(key);
-        c = flat / HW;
-        const int rem = flat - c * HW;
-        const int yi = rem / p.W;
-        const int xi = rem - yi * p.W;
-        mx = __fadd_rn(static_cast<float>(xi), sigmoid_cold(gbuf[lane]));
-        my = __fadd_rn(static_cast<float>(yi), sigmoid_cold(gbuf[32 + lane]));
-        lo_x = lo_y = INFINITY;
-        hi_x = hi_y = -INFINITY;
-      }
-      float* vout = p.verts + row * V * 2;
-#pragma unroll 1
-      for (int v = 0; v < V; ++v) {
-        float vx = 0.f, vy = 0.f;
-        if (valid) {
-          vx = __fmul_rn(p.down, __fadd_rn(gbuf[(2 + 2 * v) * 32 + lane], mx));
-          vy = __fmul_rn(p.down, __fadd_rn(gbuf[(3 + 2 * v) * 32 + lane], my));
-          lo_x = fminf(lo_x, vx); hi_x = fmaxf(hi_x, vx);
-          lo_y = fminf(lo_y, vy); hi_y = fmaxf(hi_y, vy);
-        }
-        vout[2 * v] = vx;
-        vout[2 * v + 1] = vy;
-      }
-      p.cls[row] = c;
-      p.score[row] = sc;
-      p.proj[row * 2 + 0] = valid ? __fmul_rn(p.down, mx) : 0.f;
-      p.proj[row * 2 + 1] = valid ? __fmul_rn(p.down, my) : 0.f;
-      p.bbox[row * 4 + 0] = lo_x;
-      p.bbox[row * 4 + 1] = lo_y;
-      p.bbox[row * 4 + 2] = hi_x;
-      p.bbox[row * 4 + 3] = hi_y;
-      if (p.flat) p.flat[row] = flat;
-    }
-    __syncwarp();
+  for (int j = lane; j < K; j += 32) {
+    const size_t row = static_cast<size_t>(b) * K + j;
+    const bool valid = j < cnt;
+    const unsigned long long key = valid ? sorted[j] : 0ull;
+    p.score[row] = valid ? key_score(key) : 0.f;
+    p.flat[row] = valid ? static_cast<int32_t>(key_flat(key)) : -1;
   }
   if (lane == 0) p.counts[b] = cnt;
 }
 
-// Tier B rows of plane (b,c): index split + sub-pixel add (models/model.py:113-114 and the commented :55-57).  Rows
-// cnt..K-1 are 0.0-score fillers = the lowest flat indices that are not positive-score peaks (what a top-K over the
-// zero-filled peak map returns).  scratch: >= 3K+8 words of shared memory of this warp.
-template <typename T>
-static __device__ __noinline__ void warp_emit_kpt(const PlaneParams& p, int b, int c, const unsigned long long* sorted, int cnt,
-                                                  uint32_t* scratch, int lane) {
+// Tier B selection of plane (b,c): score and flat index of the K candidates.  Rows cnt..K-1 are 0.0-score fillers = the
+// lowest flat indices that are not positive-score peaks (what a top-K over the zero-filled peak map returns, SURVEY
+// App. A).  The sub-pixel add (models/model.py:113-114, :55-57) runs afterwards in epilogue_kpt_kernel.
+//   scratch: >= 3K+8 words of shared memory of this warp.
+static __device__ __noinline__ void warp_write_kpt(const PlaneParams& p, int b, int c, const unsigned long long* sorted, int cnt,
+                                                   uint32_t* scratch, int lane) {
   const int K = p.K, HW = p.H * p.W;
   uint32_t* fill = scratch + 2 * K;             // [K] filler indices (rows cnt..K-1)
   if (cnt < K) {
@@ -606,41 +547,11 @@ static __device__ __noinline__ void warp_emit_kpt(const PlaneParams& p, int b, i
     }
     __syncwarp();
   }
-  // phase 1: gather the two sub-pixel logits of every row into shared memory (4 rows per lane in flight)
-  float* g0 = reinterpret_cast<float*>(scratch);          // [K]   (the `taken` flags are dead by now)
-  float* g1 = g0 + K;                                      // [K]
-  const T* off2 = reinterpret_cast<const T*>(p.off2_kpt) + static_cast<size_t>(b) * 2 * HW;
 #pragma unroll 1
-  for (int j0 = lane; j0 < K; j0 += 32 * 4) {
-    float r0[4], r1[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = j0 + 32 * u;
-      r0[u] = r1[u] = 0.f;
-      if (j < K) {
-        const uint32_t flat = j < cnt ? key_flat(sorted[j]) : fill[j];
-        r0[u] = to_f32(off2[flat]);
-        r1[u] = to_f32(off2[HW + flat]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = j0 + 32 * u;
-      if (j < K) { g0[j] = r0[u]; g1[j] = r1[u]; }
-    }
-  }
-  __syncwarp();
-  // phase 2
-#pragma unroll 2
   for (int j = lane; j < K; j += 32) {
-    const uint32_t flat = j < cnt ? key_flat(sorted[j]) : fill[j];
-    const int yi = flat / p.W;
-    const int xi = flat - yi * p.W;
     const size_t row = (static_cast<size_t>(b) * p.Cv + c) * K + j;
     p.kscore[row] = j < cnt ? key_score(sorted[j]) : 0.0f;
-    p.kxy[row * 2 + 0] = __fadd_rn(static_cast<float>(xi), sigmoid_cold(g0[j]));
-    p.kxy[row * 2 + 1] = __fadd_rn(static_cast<float>(yi), sigmoid_cold(g1[j]));
-    p.kflat[row] = static_cast<int32_t>(flat);
+    p.kflat[row] = static_cast<int32_t>(j < cnt ? key_flat(sorted[j]) : fill[j]);
   }
   __syncwarp();
 }
@@ -694,7 +605,9 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
   __syncthreads();
 
   const int planes_per_img = p.C + p.Cv;
-  const int per_img = planes_per_img * g.split;
+  const int slots_per_img = (p.C > 0 ? 1 : 0) + p.Cv;
+  const int per_img = slots_per_img * g.split;
+  auto plane_of_slot = [&](int slot) { return (p.C > 0 && slot == 0) ? 0 : p.C + slot - (p.C > 0 ? 1 : 0); };
   // speculative start threshold for a plane index: a few bins below the boundary remembered for it, or for its segment
   auto spec_for_plane = [&](int pl) -> int {
     if (pl >= kMaxPlanes) return -1;
@@ -712,7 +625,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
     // the first items of this CTA start from what the previous launch remembered
     for (int q = 0; q < kNBuf; ++q) {
       const long long item = static_cast<long long>(blockIdx.x) + static_cast<long long>(q) * gridDim.x;
-      if (item < g.n_items) ctl.sel[q].spec_bin = spec_for_plane(static_cast<int>((item % per_img) >> g.split_shift));
+      if (item < g.n_items) ctl.sel[q].spec_bin = spec_for_plane(plane_of_slot(static_cast<int>((item % per_img) >> g.split_shift)));
     }
   }
   __syncthreads();
@@ -743,6 +656,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
         for (; ii.item < g.n_items; ii.next()) {
           if (pass == 1 && __ldcg(&p.retry[ii.item]) == 0u) continue;
           const ItemInfo it = decode_item(p, g, ii, static_cast<int>(sizeof(T)));
+          int qq = 0, pli = 0;                          // chunk within the plane, plane within the item
           for (int q = 0; q < it.nchunks; ++q, ++gq) {
             const uint32_t s = gq & smask;
             if (gq >= static_cast<uint32_t>(S)) {
@@ -750,7 +664,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
               pl::mbar_wait(pl::smem_u32(&ctl.empty[s]), ((gq >> sshift) - 1u) & 1u, p.status, 0xE1000001u, 32);
               RTM3D_ACC(kStProdWait, RTM3D_CLK() - w0);
             }
-            const int c_lo = it.ys + q * g.chunk_rows, c_hi = min(c_lo + g.chunk_rows, it.ye);
+            const int c_lo = it.ys + qq * g.chunk_rows, c_hi = min(c_lo + g.chunk_rows, it.ye);
             const int top = max(c_lo - 1, 0), bot = min(c_hi + 1, H);      // rows [top, bot) incl. the halo rows
             const uint32_t bytes = static_cast<uint32_t>(bot - top) * g.row_bytes;
             // stage row r holds image row (c_lo - 1 + r): a missing top halo leaves stage row 0 unused
@@ -760,7 +674,8 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
             ctl.wl_next[s] = 0u;                        // every B-warp has left the stage (empty) / nobody has entered it yet
             RTM3D_TRACE(8);
             pl::mbar_arrive_expect_tx(bar, bytes);
-            pl::bulk_g2s(dst, it.base + static_cast<size_t>(top) * g.row_bytes, bytes, bar);
+            pl::bulk_g2s(dst, it.base + static_cast<size_t>(pli) * it.plane_bytes + static_cast<size_t>(top) * g.row_bytes, bytes, bar);
+            if (++qq == it.cpp) { qq = 0; ++pli; }
           }
         }
         RTM3D_FLUSH(kStProdWait);
@@ -789,6 +704,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
           if (sb >= 1) t_floor = fmaxf(t_floor, filter_from_bin(sb));
         }
         if (lane == 0) RTM3D_ACC(kStASetup, RTM3D_CLK() - as0);
+        int qq = 0;                                     // chunk within the plane
         for (int q = 0; q < it.nchunks; ++q, ++gq) {
           const uint32_t s = gq & smask;
           {
@@ -798,7 +714,8 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
           }
           const long long al0 = RTM3D_CLK();
           if (warp == kAWarp0) RTM3D_TRACE(1);
-          const int c_lo = it.ys + q * g.chunk_rows, c_hi = min(c_lo + g.chunk_rows, it.ye);
+          const int c_lo = it.ys + qq * g.chunk_rows, c_hi = min(c_lo + g.chunk_rows, it.ye);
+          if (++qq == it.cpp) qq = 0;
           const unsigned char* centre = ring + static_cast<size_t>(s) * g.stage_bytes + g.row_bytes;  // image row c_lo
           const int aw = warp - kAWarp0;
           // this A-warp's private segment of the stage's worklist: no atomics, the fill count lives in a register
@@ -867,6 +784,8 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
           const int sb = L.spec_bin;
           if (sb >= 1) t_floor = fmaxf(t_floor, filter_from_bin(sb));
         }
+        int qq = 0;                                     // chunk within the plane
+        uint32_t flat_base = it.flat_base;              // of the plane the chunk belongs to
         for (int q = 0; q < it.nchunks; ++q, ++gq) {
           const uint32_t s = gq & smask;
           {
@@ -875,7 +794,9 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
             if (lane == 0) RTM3D_ACC(kStWaitScanned, RTM3D_CLK() - w0);
           }
           const long long bb0 = RTM3D_CLK();
-          const int c_lo = it.ys + q * g.chunk_rows;
+          const int c_lo = it.ys + qq * g.chunk_rows;
+          const uint32_t chunk_flat_base = flat_base;
+          if (++qq == it.cpp) { qq = 0; flat_base += it.hw; }
           const unsigned short* wl = wl_all + static_cast<size_t>(s) * g.wl_cap;
           const unsigned char* centre = ring + static_cast<size_t>(s) * g.stage_bytes + g.row_bytes;
           // the stage's worklist = the concatenation of the A-warps' segments
@@ -948,7 +869,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
                 // sigmoid_ref is monotone (tests/test_sigmoid_gpu.py sweeps every float): the largest neighbour decides
                 if (cand && neighbour_needs_exact(xn, xc) && sigmoid_cold(xn) > sc) cand = false;
                 if (cand) {
-                  const uint32_t flat = it.flat_base + static_cast<uint32_t>(y) * W + static_cast<uint32_t>(c4 * E + i);
+                  const uint32_t flat = chunk_flat_base + static_cast<uint32_t>(y) * W + static_cast<uint32_t>(c4 * E + i);
                   const unsigned long long key = make_key(sc, flat);
                   if (key >= kstar) {
                     const uint32_t slot = atomicAdd(const_cast<uint32_t*>(&L.reserve), 1u);
@@ -1105,7 +1026,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
           if (g.speculate && pass == 0 && nxt < g.n_items) {
             int rn = ii.r + kNBuf * ii.step_r;
             while (rn >= per_img) rn -= per_img;
-            nsb = spec_for_plane(rn >> g.split_shift);
+            nsb = spec_for_plane(plane_of_slot(rn >> g.split_shift));
           }
           L.spec_bin = nsb;
           __threadfence_block();
@@ -1131,8 +1052,8 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
         if (g.debug == 5) continue;
 
         // ---- emit, or publish + merge by the last part of the problem
-        const int parts = it.is_main ? p.C * g.split : g.split;
-        const int kc = it.plane - p.C;
+        const int parts = g.split;                     // strips of the problem (image, or keypoint plane)
+        const int kc = it.kc;
         bool do_emit = true;
         if (parts > 1) {
           const size_t unit = static_cast<size_t>(item);
@@ -1152,8 +1073,8 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
           do_emit = last != 0;
           if (do_emit) {
             __threadfence();
-            // units of this problem are contiguous items: main planes 0..C-1 (x split), or the strips of one kpt plane
-            const size_t unit0 = static_cast<size_t>(it.b) * per_img + (it.is_main ? 0 : static_cast<size_t>(it.plane) * g.split);
+            // units of this problem are contiguous items: the strips of the image's main item, or of one keypoint plane
+            const size_t unit0 = static_cast<size_t>(it.b) * per_img + static_cast<size_t>(it.slot) * g.split;
             // gather the parts' sorted lists into finA at offsets u*K, then rank-merge into finB
             int total = 0;
 #pragma unroll 1
@@ -1207,8 +1128,8 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
         RTM3D_FIN_LAP(kStFinPublish);
         if (g.debug == 6 || (g.debug == 9 && it.is_main) || (g.debug == 10 && !it.is_main)) continue;
         if (do_emit) {
-          if (it.is_main) warp_emit_main<T>(sp, it.b, finB, have, reinterpret_cast<float*>(fin_scratch), lane);
-          else warp_emit_kpt<T>(sp, it.b, kc, finB, have, fin_scratch, lane);
+          if (it.is_main) warp_write_main(sp, it.b, finB, have, lane);
+          else warp_write_kpt(sp, it.b, kc, finB, have, fin_scratch, lane);
         }
         __syncwarp();
         RTM3D_FIN_LAP(kStFinEmit);
@@ -1250,7 +1171,7 @@ static bool make_plane_geom(const PlaneParams& p, int dtype, int split_override,
     }
     g_sm_count = n;
   }
-  const long long planes = static_cast<long long>(p.B) * (p.C + p.Cv);
+  const long long planes = static_cast<long long>(p.B) * ((p.C > 0 ? 1 : 0) + p.Cv);   // items per strip index (the C main planes are one item)
   // strips per plane: enough items to fill the chip and a last wave that is not mostly idle
   int split = 1;
   if (split_override > 0) {
@@ -1265,9 +1186,7 @@ static bool make_plane_geom(const PlaneParams& p, int dtype, int split_override,
     }
   }
   while (split > 1 && p.H < split) split /= 2;
-  int max_parts = 1;
-  if (p.C > 0 && p.C * split > max_parts) max_parts = p.C * split;
-  if (p.Cv > 0 && split > max_parts) max_parts = split;
+  const int max_parts = split;
   g.split = split;
   g.split_shift = split == 8 ? 3 : split == 4 ? 2 : split == 2 ? 1 : 0;
   g.row_bytes = row_bytes;
@@ -1278,10 +1197,9 @@ static bool make_plane_geom(const PlaneParams& p, int dtype, int split_override,
   int fin = max_parts * p.K;
   if (fin < p.K + 96) fin = p.K + 96;
   g.fin_cap = (fin + 31) & ~31;
-  // finA doubles as the emit scratch: 3K+8 words (keypoint fillers / gathers) or 32*(2V+2) floats (Tier A gathers)
+  // finA doubles as the filler scratch of the keypoint planes: 3K+8 words
   {
-    int words = 3 * p.K + 8;
-    if (words < 32 * (2 * p.n_vert + 2)) words = 32 * (2 * p.n_vert + 2);
+    const int words = 3 * p.K + 8;
     if (g.fin_cap * 2 < words) g.fin_cap = ((words + 1) / 2 + 31) & ~31;
   }
   const size_t fixed = static_cast<size_t>(kNBuf) * kHistBins * 4 + static_cast<size_t>(kNBuf) * g.list_cap * 8 +
@@ -1320,7 +1238,7 @@ static bool make_plane_geom(const PlaneParams& p, int dtype, int split_override,
     g.wl_seg = per_warp * 32;
     g.wl_cap = kAWarps * g.wl_seg;
   }
-  g.n_items = static_cast<int>(planes * split);
+  g.n_items = static_cast<int>(static_cast<long long>(p.B) * ((p.C > 0 ? 1 : 0) + p.Cv) * split);
   g.smem = static_cast<unsigned>(static_cast<size_t>(stages) * (g.stage_bytes + 2ull * g.wl_cap) + fixed);
   return g.smem <= 227 * 1024 - 4096;
 }

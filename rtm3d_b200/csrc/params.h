@@ -54,7 +54,7 @@ struct PlaneParams {
 };
 
 struct WorkspaceLayout {
-  size_t tickets_off, status_off, keys_off, counts_off, retry_off, guess_off, total;
+  size_t tickets_off, status_off, keys_off, counts_off, retry_off, guess_off, flat_off, total;
   int strip_rows, nstrips, list_cap;
   size_t generic_smem;
 };

@@ -6,6 +6,104 @@
 namespace rtm3d {
 
 // ---------------------------------------------------------------------------------------------------------------
+// Tier A epilogue (models/model.py:47-50 gather + sub-pixel add, :63-73 regress / scale / 2D box) for the rows the
+// plane-streaming kernel selected: one thread per (detection, vertex), wide over the whole batch so that the scattered
+// 4-byte gathers of the regression planes are latency-hidden by occupancy instead of stalling the streaming kernel.
+// Rows >= counts[b] are zero-filled (cls = -1).
+template <typename T>
+__global__ void __launch_bounds__(256) epilogue_main_kernel(const EpiMainParams p, int vp, int vp_shift) {
+  const int b = blockIdx.y;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = idx >> vp_shift, v = idx & (vp - 1);
+  const int V = p.n_vert, K = p.K, HW = p.H * p.W;
+  const bool row_ok = j < K;
+  const size_t row = static_cast<size_t>(b) * K + (row_ok ? j : 0);
+  const bool valid = row_ok && j < p.counts[b];
+  const bool vert = v < V;
+  float vx = 0.f, vy = 0.f, mx = 0.f, my = 0.f;
+  int c = -1;
+  if (valid) {
+    const int flat = p.flat[row];
+    c = flat / HW;
+    const int rem = flat - c * HW;
+    const int yi = rem / p.W;
+    const int xi = rem - yi * p.W;
+    const T* off2 = reinterpret_cast<const T*>(p.off2) + static_cast<size_t>(b) * 2 * HW;
+    const T* off = reinterpret_cast<const T*>(p.off) + static_cast<size_t>(b) * 2 * V * HW;
+    const float r0 = to_f32(off2[rem]);
+    const float r1 = to_f32(off2[HW + rem]);
+    float ox = 0.f, oy = 0.f;
+    if (vert) {
+      ox = to_f32(off[static_cast<size_t>(2 * v) * HW + rem]);
+      oy = to_f32(off[static_cast<size_t>(2 * v + 1) * HW + rem]);
+    }
+    mx = __fadd_rn(static_cast<float>(xi), sigmoid_ref(r0));
+    my = __fadd_rn(static_cast<float>(yi), sigmoid_ref(r1));
+    vx = __fmul_rn(p.down, __fadd_rn(ox, mx));
+    vy = __fmul_rn(p.down, __fadd_rn(oy, my));
+  }
+  float lo_x = (valid && vert) ? vx : INFINITY, hi_x = (valid && vert) ? vx : -INFINITY;
+  float lo_y = (valid && vert) ? vy : INFINITY, hi_y = (valid && vert) ? vy : -INFINITY;
+  for (int d = 1; d < vp; d <<= 1) {
+    lo_x = fminf(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, d));
+    hi_x = fmaxf(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, d));
+    lo_y = fminf(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, d));
+    hi_y = fmaxf(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, d));
+  }
+  if (!row_ok) return;
+  if (vert) {
+    float* vout = p.verts + (row * V + v) * 2;
+    vout[0] = valid ? vx : 0.f;
+    vout[1] = valid ? vy : 0.f;
+  }
+  if (v == 0) {
+    p.cls[row] = c;
+    p.proj[row * 2 + 0] = valid ? __fmul_rn(p.down, mx) : 0.f;
+    p.proj[row * 2 + 1] = valid ? __fmul_rn(p.down, my) : 0.f;
+    p.bbox[row * 4 + 0] = valid ? lo_x : 0.f;
+    p.bbox[row * 4 + 1] = valid ? lo_y : 0.f;
+    p.bbox[row * 4 + 2] = valid ? hi_x : 0.f;
+    p.bbox[row * 4 + 3] = valid ? hi_y : 0.f;
+  }
+}
+
+int launch_epilogue_main(const EpiMainParams& p, int dtype, cudaStream_t s) {
+  int vp = 1, sh = 0;
+  while (vp < p.n_vert) { vp <<= 1; ++sh; }
+  const int threads = p.K * vp;
+  dim3 grid((threads + 255) / 256, p.B);
+  if (dtype == 0) epilogue_main_kernel<float><<<grid, 256, 0, s>>>(p, vp, sh);
+  else epilogue_main_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(p, vp, sh);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// Tier B epilogue: index split + sub-pixel add (models/model.py:113-114 and the commented :55-57), one thread per candidate.
+template <typename T>
+__global__ void __launch_bounds__(256) epilogue_kpt_kernel(const EpiKptParams p) {
+  const size_t n = static_cast<size_t>(p.B) * p.Cv * p.K;
+  const size_t row = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (row >= n) return;
+  const int HW = p.H * p.W;
+  const int b = static_cast<int>(row / (static_cast<size_t>(p.Cv) * p.K));
+  const int flat = p.kflat[row];
+  const int yi = flat / p.W;
+  const int xi = flat - yi * p.W;
+  const T* off2 = reinterpret_cast<const T*>(p.voff2) + static_cast<size_t>(b) * 2 * HW;
+  const float r0 = to_f32(off2[flat]);
+  const float r1 = to_f32(off2[HW + flat]);
+  p.kxy[row * 2 + 0] = __fadd_rn(static_cast<float>(xi), sigmoid_ref(r0));
+  p.kxy[row * 2 + 1] = __fadd_rn(static_cast<float>(yi), sigmoid_ref(r1));
+}
+
+int launch_epilogue_kpt(const EpiKptParams& p, int dtype, cudaStream_t s) {
+  const size_t n = static_cast<size_t>(p.B) * p.Cv * p.K;
+  const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+  if (dtype == 0) epilogue_kpt_kernel<float><<<grid, 256, 0, s>>>(p);
+  else epilogue_kpt_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // _group_vertexs_kf (models/model.py:134-162).  One CTA per image; thread per (detection n, channel k).
 //   rel  = v_kj - m_n                 (:147)      diff = rel - off_kn        (:149)
 //   dist = diff_x^2 + diff_y^2        (:150)      j*   = argmin_j, first minimal index (:151)

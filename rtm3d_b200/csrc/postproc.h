@@ -21,6 +21,21 @@ struct Box3dParams {
   float* loc; float* dim; float* alpha; float* rot_y; float* corners2d;
 };
 
+// Tier A epilogue after the plane-streaming kernel: rows (flat, counts) -> cls, proj, verts, bbox.
+struct EpiMainParams {
+  const int32_t* flat; const int32_t* counts; const void* off; const void* off2;
+  int B, C, H, W, n_vert, K;
+  float down;
+  int64_t* cls; float* proj; float* verts; float* bbox;
+};
+// Tier B epilogue after the plane-streaming kernel: candidate index -> sub-pixel position.
+struct EpiKptParams {
+  const int32_t* kflat; const void* voff2;
+  int B, Cv, H, W, K;
+  float* kxy;
+};
+int launch_epilogue_main(const EpiMainParams& p, int dtype, cudaStream_t s);
+int launch_epilogue_kpt(const EpiKptParams& p, int dtype, cudaStream_t s);
 int launch_group(const GroupParams& p, int dtype, cudaStream_t s);
 int launch_box3d(const Box3dParams& p, int dtype, cudaStream_t s);
 int launch_sigmoid(const float* x, float* y, size_t n, cudaStream_t s);
