@@ -195,7 +195,9 @@ def run_b200(args, w):
     nsets = 2
     sets = [make_inputs(torch, w, dev, 1234 + rank + 100 * s) for s in range(nsets)]
     heat_bytes = B * (w["C"] + Cv) * w["H"] * w["W"] * 4
-    launches_per_step = 2 if Cv else 1      # fused plane-streaming kernel (+ grouping kernel)
+    # kernels per step: plane-streaming kernel + fused post kernel (main only: + Tier A epilogue)
+    launches_per_step = 2
+    marks_per_step = 3 if Cv else 2          # events: before, after the plane kernel, after the post kernel
 
     gather_out = None
 
@@ -249,8 +251,8 @@ def run_b200(args, w):
     ms_step = ms_total / args.steps
 
     # per-kernel durations from the marks (each step: before, after main, [after kpt, after group])
-    per = launches_per_step + 1
-    names = ["decode_planes(main+kpt)", "group_vertices"] if Cv else ["decode_planes(main)"]
+    per = marks_per_step
+    names = ["decode_planes(main+kpt)", "post_fused"] if Cv else ["decode_planes(main)+epilogue"]
     kernel_ms = {n: 0.0 for n in names}
     for s in range(args.steps):
         for j, n in enumerate(names):

@@ -49,6 +49,8 @@ enum rtm3d_error {
 #define RTM3D_FLAG_FORCE_GENERIC 1u /* use the shape-generic strip kernels even when the plane-streaming kernel applies */
 #define RTM3D_FLAG_NO_SPECULATION 2u /* plane-streaming kernel: never start a plane at the previous plane's threshold */
 #define RTM3D_FLAG_NO_GROUP 4u /* rtm3d_decode_fused: stop after the two decodes (the caller runs rtm3d_group_vertices itself) */
+#define RTM3D_FLAG_NO_EPILOGUE 8u /* decode entry points: stop after the selection (score, flat, counts / kscore, kflat); the
+                                   caller runs rtm3d_epilogue_main / rtm3d_epilogue_keypoints itself */
 #define RTM3D_FLAG_MAX_CTAS(n) (((unsigned)(n) & 0xFFu) << 16) /* plane-streaming kernel: at most n CTAs (0 = one per SM) */
 #define RTM3D_FLAG_SPLIT(s) (((unsigned)(s) & 0xFu) << 8) /* plane-streaming kernel: force s strips (1,2,4,8) per plane; 0 = auto */
 
@@ -138,6 +140,31 @@ int rtm3d_decode_fused(const void* hm, const void* off, const void* off2, const 
                        float* kscore, float* kxy, int32_t* kflat,
                        float* kpt_proj, float* kpt_score, int32_t* kpt_j, float* verts_cv,
                        void* ws, size_t ws_bytes, unsigned flags, void* stream);
+
+/*
+ * Second halves of rtm3d_decode_main / rtm3d_decode_keypoints, enqueued by them unless RTM3D_FLAG_NO_EPILOGUE is set:
+ *   rtm3d_epilogue_main       rows (flat, counts) -> cls, proj, verts, bbox: gather of offset_fr_main / main_offset at the
+ *                             integer peak, sub-pixel add, vertex regress, x DOWN_SAMPLE, 2D box (models/model.py:47-50,
+ *                             63-73, 117-132)
+ *   rtm3d_epilogue_keypoints  kflat -> kxy: index split + sigmoid sub-pixel add (models/model.py:113-114, 55-57)
+ * One thread per (detection, vertex) / per candidate over the whole batch.
+ */
+int rtm3d_epilogue_main(const int32_t* flat, const int32_t* counts, const void* off, const void* off2, int dtype,
+                        int B, int C, int H, int W, int n_vert, int K, float down,
+                        int64_t* cls, float* proj, float* verts, float* bbox, void* stream);
+int rtm3d_epilogue_keypoints(const int32_t* kflat, const void* voff2, int dtype, int B, int Cv, int H, int W, int K,
+                             float* kxy, void* stream);
+
+/*
+ * Everything that follows the selection of rtm3d_decode_fused in ONE kernel (one CTA per image): rtm3d_epilogue_keypoints,
+ * rtm3d_epilogue_main and rtm3d_group_vertices with bit-identical results.  rtm3d_decode_fused enqueues it itself unless
+ * RTM3D_FLAG_NO_EPILOGUE / RTM3D_FLAG_NO_GROUP ask for the stages separately.
+ */
+int rtm3d_post_fused(const int32_t* flat, const int32_t* counts, const int32_t* kflat, const float* kscore,
+                     const void* off, const void* off2, const void* voff2, int dtype,
+                     int B, int C, int Cv, int H, int W, int n_vert, int K, float down,
+                     int64_t* cls, float* proj, float* verts, float* bbox, float* kxy,
+                     float* kpt_proj, float* kpt_score, int32_t* kpt_j, float* verts_cv, void* stream);
 
 /*
  * Tier B -- _group_vertexs_kf (models/model.py:134-162): for every detection n of rtm3d_decode_main and keypoint

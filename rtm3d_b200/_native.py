@@ -15,6 +15,7 @@ F32, BF16 = 0, 1
 FLAG_FORCE_GENERIC = 1
 FLAG_NO_SPECULATION = 2
 FLAG_NO_GROUP = 4
+FLAG_NO_EPILOGUE = 8
 
 _c = ctypes
 _vp, _i, _f, _sz, _u = _c.c_void_p, _c.c_int, _c.c_float, _c.c_size_t, _c.c_uint
@@ -34,6 +35,10 @@ SIGNATURES = {
     "rtm3d_decode_keypoints_host": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _u, _vp],
     "rtm3d_decode_fused": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f,
                            _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _u, _vp],
+    "rtm3d_epilogue_main": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp],
+    "rtm3d_epilogue_keypoints": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "rtm3d_post_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f,
+                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "rtm3d_group_vertices": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp],
     "rtm3d_sigmoid_f32": [_vp, _vp, _sz, _vp],
     "rtm3d_threshold_table": [_vp, _vp, _i, _c.POINTER(_i), _vp],

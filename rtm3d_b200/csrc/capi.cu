@@ -61,7 +61,8 @@ void carve(rtm3d::DecodeParams& p, const rtm3d::WorkspaceLayout& L, void* ws) {
 }
 
 // The wide epilogue kernels that follow the plane-streaming kernel (it writes score / flat / counts and kscore / kflat).
-int launch_epilogues(const rtm3d::PlaneParams& q, int dtype, cudaStream_t s) {
+int launch_epilogues(const rtm3d::PlaneParams& q, int dtype, unsigned flags, cudaStream_t s) {
+  if (flags & RTM3D_FLAG_NO_EPILOGUE) return 0;
   if (q.C > 0) {
     rtm3d::EpiMainParams e{q.flat, q.counts, q.off, q.off2_main, q.B, q.C, q.H, q.W, q.n_vert, q.K, q.down, q.cls, q.proj, q.verts, q.bbox};
     if (int r = cuda_fail(rtm3d::launch_epilogue_main(e, dtype, s), "Tier A epilogue launch")) return r;
@@ -96,7 +97,7 @@ int dispatch(rtm3d::DecodeParams& p, const rtm3d::WorkspaceLayout& L, int dtype,
                                         static_cast<int>((flags >> 16) & 0xFFu), static_cast<int>((flags >> 24) & 0xFu), s);   // -1000: shape not eligible
     if (rc != -1000) {
       if (int e = cuda_fail(rc, "decode (plane-streaming kernel) launch")) return e;
-      return launch_epilogues(q, dtype, s);
+      return launch_epilogues(q, dtype, flags, s);
     }
   }
   if (L.generic_smem > 200 * 1024) return fail(RTM3D_ERR_SHAPE, "row too wide for the generic kernel (%zu B smem)", L.generic_smem);
@@ -282,8 +283,15 @@ int rtm3d_decode_fused(const void* hm, const void* off, const void* off2, const 
                                         static_cast<int>((flags >> 16) & 0xFFu), static_cast<int>((flags >> 24) & 0xFu), s);
     if (rc != -1000) {
       if (int e = cuda_fail(rc, "decode (plane-streaming kernel, fused) launch")) return e;
-      if (int e = launch_epilogues(q, dtype, s)) return e;
       fused = true;
+      // everything after the selection in one kernel, unless the caller wants the stages separately (bench.py's marks)
+      if (!(flags & (RTM3D_FLAG_NO_EPILOGUE | RTM3D_FLAG_NO_GROUP)) &&
+          rtm3d::post_fused_smem(Cv, K, n_vert) <= 200 * 1024) {
+        rtm3d::PostFusedParams f{flat, counts, kflat, kscore, off, off2, voff2, B, C, Cv, H, W, n_vert, K, down,
+                                 cls, proj, verts, bbox, kxy, kpt_proj, kpt_score, kpt_j, verts_cv};
+        return cuda_fail(rtm3d::launch_post_fused(f, dtype, s), "fused post kernel launch");
+      }
+      if (int e = launch_epilogues(q, dtype, flags, s)) return e;
     }
   }
   if (!fused) {
@@ -297,6 +305,43 @@ int rtm3d_decode_fused(const void* hm, const void* off, const void* off2, const 
   if (flags & RTM3D_FLAG_NO_GROUP) return 0;
   return rtm3d_group_vertices(flat, counts, off, off2, dtype, B, H, W, n_vert, K, kscore, kxy, Cv, down, kpt_proj, kpt_score,
                               kpt_j, verts_cv, stream);
+}
+
+int rtm3d_epilogue_main(const int32_t* flat, const int32_t* counts, const void* off, const void* off2, int dtype, int B, int C,
+                        int H, int W, int n_vert, int K, float down, int64_t* cls, float* proj, float* verts, float* bbox,
+                        void* stream) {
+  if (!flat || !counts || !off || !off2 || !cls || !proj || !verts || !bbox) return fail(RTM3D_ERR_NULL, "NULL pointer argument");
+  if (dtype != RTM3D_F32 && dtype != RTM3D_BF16) return fail(RTM3D_ERR_DTYPE, "dtype %d", dtype);
+  if (int e = check_shape(B, C, H, W, K)) return e;
+  if (n_vert < 1 || n_vert > RTM3D_MAX_VERTS) return fail(RTM3D_ERR_SHAPE, "n_vert=%d outside [1,%d]", n_vert, RTM3D_MAX_VERTS);
+  rtm3d::EpiMainParams e{flat, counts, off, off2, B, C, H, W, n_vert, K, down, cls, proj, verts, bbox};
+  return cuda_fail(rtm3d::launch_epilogue_main(e, dtype, static_cast<cudaStream_t>(stream)), "Tier A epilogue launch");
+}
+
+int rtm3d_epilogue_keypoints(const int32_t* kflat, const void* voff2, int dtype, int B, int Cv, int H, int W, int K, float* kxy,
+                             void* stream) {
+  if (!kflat || !voff2 || !kxy) return fail(RTM3D_ERR_NULL, "NULL pointer argument");
+  if (dtype != RTM3D_F32 && dtype != RTM3D_BF16) return fail(RTM3D_ERR_DTYPE, "dtype %d", dtype);
+  if (int e = check_shape(B, Cv, H, W, K)) return e;
+  rtm3d::EpiKptParams e{kflat, voff2, B, Cv, H, W, K, kxy};
+  return cuda_fail(rtm3d::launch_epilogue_kpt(e, dtype, static_cast<cudaStream_t>(stream)), "Tier B epilogue launch");
+}
+
+int rtm3d_post_fused(const int32_t* flat, const int32_t* counts, const int32_t* kflat, const float* kscore, const void* off,
+                     const void* off2, const void* voff2, int dtype, int B, int C, int Cv, int H, int W, int n_vert, int K,
+                     float down, int64_t* cls, float* proj, float* verts, float* bbox, float* kxy, float* kpt_proj,
+                     float* kpt_score, int32_t* kpt_j, float* verts_cv, void* stream) {
+  if (!flat || !counts || !kflat || !kscore || !off || !off2 || !voff2 || !cls || !proj || !verts || !bbox || !kxy || !kpt_proj ||
+      !kpt_score || !kpt_j)
+    return fail(RTM3D_ERR_NULL, "NULL pointer argument");
+  if (dtype != RTM3D_F32 && dtype != RTM3D_BF16) return fail(RTM3D_ERR_DTYPE, "dtype %d", dtype);
+  if (int e = check_shape(B, C, H, W, K)) return e;
+  if (Cv < 1) return fail(RTM3D_ERR_SHAPE, "Cv=%d", Cv);
+  if (n_vert < 1 || n_vert > RTM3D_MAX_VERTS) return fail(RTM3D_ERR_SHAPE, "n_vert=%d outside [1,%d]", n_vert, RTM3D_MAX_VERTS);
+  if (rtm3d::post_fused_smem(Cv, K, n_vert) > 200 * 1024) return fail(RTM3D_ERR_SHAPE, "Cv*K too large for one CTA");
+  rtm3d::PostFusedParams f{flat, counts, kflat, kscore, off, off2, voff2, B, C, Cv, H, W, n_vert, K, down,
+                           cls, proj, verts, bbox, kxy, kpt_proj, kpt_score, kpt_j, verts_cv};
+  return cuda_fail(rtm3d::launch_post_fused(f, dtype, static_cast<cudaStream_t>(stream)), "fused post kernel launch");
 }
 
 int rtm3d_group_vertices(const int32_t* flat, const int32_t* counts, const void* off, const void* off2, int dtype, int B,

@@ -104,6 +104,134 @@ int launch_epilogue_kpt(const EpiKptParams& p, int dtype, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Fused post kernel of rtm3d_decode_fused: for one image, (1) Tier B epilogue of its Cv*K candidates (kept in shared
+// memory for the grouping), (2) per (detection n, channel k): the Tier A gathers / regress and the nearest-candidate
+// search of _group_vertexs_kf, (3) per detection: 2D box, class, centre.  Arithmetic and association order are those of
+// epilogue_main_kernel, epilogue_kpt_kernel and group_vertices_kernel (bit-identical results).
+constexpr int kPostThreads = 512;
+template <typename T>
+__global__ void __launch_bounds__(kPostThreads) post_fused_kernel(const PostFusedParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int K = p.K, Cv = p.Cv, V = p.n_vert, HW = p.H * p.W;
+  float* s_xy = reinterpret_cast<float*>(smem_raw);                 // [Cv*K*2] candidate positions
+  float* s_v = s_xy + static_cast<size_t>(Cv) * K * 2;               // [K*V*2]  scaled regressed vertices (Tier A)
+  float* s_m = s_v + static_cast<size_t>(K) * V * 2;                 // [K*2]    unscaled centre (mx, my)
+  const int n_det = p.counts[b];
+  const T* voff2 = reinterpret_cast<const T*>(p.voff2) + static_cast<size_t>(b) * 2 * HW;
+  const T* off2 = reinterpret_cast<const T*>(p.off2) + static_cast<size_t>(b) * 2 * HW;
+  const T* off = reinterpret_cast<const T*>(p.off) + static_cast<size_t>(b) * 2 * V * HW;
+  // ---- (1) candidates: index split + sub-pixel add (models/model.py:113-114, :55-57)
+  for (int i = tid; i < Cv * K; i += kPostThreads) {
+    const size_t row = static_cast<size_t>(b) * Cv * K + i;
+    const int flat = p.kflat[row];
+    const int yi = flat / p.W, xi = flat - yi * p.W;
+    const float x = __fadd_rn(static_cast<float>(xi), sigmoid_ref(to_f32(voff2[flat])));
+    const float y = __fadd_rn(static_cast<float>(yi), sigmoid_ref(to_f32(voff2[HW + flat])));
+    s_xy[2 * i] = x; s_xy[2 * i + 1] = y;
+    p.kxy[row * 2] = x; p.kxy[row * 2 + 1] = y;
+  }
+  // ---- centres of the detections (models/model.py:48-50)
+  for (int n = tid; n < K; n += kPostThreads) {
+    float mx = 0.f, my = 0.f;
+    if (n < n_det) {
+      const int rem = p.flat[static_cast<size_t>(b) * K + n] % HW;
+      const int yi = rem / p.W, xi = rem - yi * p.W;
+      mx = __fadd_rn(static_cast<float>(xi), sigmoid_ref(to_f32(off2[rem])));
+      my = __fadd_rn(static_cast<float>(yi), sigmoid_ref(to_f32(off2[HW + rem])));
+    }
+    s_m[2 * n] = mx; s_m[2 * n + 1] = my;
+  }
+  __syncthreads();
+  // ---- (2) per (detection, channel): vertex regress (models/model.py:63-69) + nearest candidate (:144-161)
+  const int KC = (Cv > V ? Cv : V);                                   // channels that need work per detection
+  for (int w = tid; w < K * KC; w += kPostThreads) {
+    const int n = w / KC, k = w - n * KC;
+    const bool valid = n < n_det;
+    float ox = 0.f, oy = 0.f, mx = 0.f, my = 0.f;
+    if (valid) {
+      const int rem = p.flat[static_cast<size_t>(b) * K + n] % HW;
+      mx = s_m[2 * n]; my = s_m[2 * n + 1];
+      if (k < V) {
+        ox = to_f32(off[static_cast<size_t>(2 * k) * HW + rem]);
+        oy = to_f32(off[static_cast<size_t>(2 * k + 1) * HW + rem]);
+      }
+    }
+    const float vx = valid ? __fmul_rn(p.down, __fadd_rn(ox, mx)) : 0.f;
+    const float vy = valid ? __fmul_rn(p.down, __fadd_rn(oy, my)) : 0.f;
+    if (k < V) {
+      s_v[(n * V + k) * 2] = vx; s_v[(n * V + k) * 2 + 1] = vy;
+      float* vout = p.verts + ((static_cast<size_t>(b) * K + n) * V + k) * 2;
+      vout[0] = vx; vout[1] = vy;
+    }
+    if (k < Cv) {
+      const size_t row = (static_cast<size_t>(b) * K + n) * Cv + k;
+      if (!valid) {
+        p.kpt_proj[row * 2] = 0.f; p.kpt_proj[row * 2 + 1] = 0.f;
+        p.kpt_score[row] = 0.f;
+        p.kpt_j[row] = -1;
+        if (p.verts_cv) { p.verts_cv[row * 2] = 0.f; p.verts_cv[row * 2 + 1] = 0.f; }
+      } else {
+        const float* cand = s_xy + static_cast<size_t>(k) * K * 2;
+        float best = INFINITY;
+        int bj = 0;
+        for (int j = 0; j < K; ++j) {
+          const float dx = __fsub_rn(__fsub_rn(cand[2 * j], mx), ox);
+          const float dy = __fsub_rn(__fsub_rn(cand[2 * j + 1], my), oy);
+          const float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+          if (d < best) { best = d; bj = j; }
+        }
+        p.kpt_proj[row * 2] = __fmul_rn(p.down, cand[2 * bj]);
+        p.kpt_proj[row * 2 + 1] = __fmul_rn(p.down, cand[2 * bj + 1]);
+        p.kpt_score[row] = p.kscore[(static_cast<size_t>(b) * Cv + k) * K + bj];
+        p.kpt_j[row] = bj;
+        if (p.verts_cv) { p.verts_cv[row * 2] = vx; p.verts_cv[row * 2 + 1] = vy; }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- (3) per detection: class, centre, 2D box over the regressed vertices (models/model.py:70-73)
+  for (int n = tid; n < K; n += kPostThreads) {
+    const size_t row = static_cast<size_t>(b) * K + n;
+    const bool valid = n < n_det;
+    float lo_x = 0.f, lo_y = 0.f, hi_x = 0.f, hi_y = 0.f;
+    int c = -1;
+    if (valid) {
+      c = p.flat[row] / HW;
+      lo_x = lo_y = INFINITY; hi_x = hi_y = -INFINITY;
+      for (int v = 0; v < V; ++v) {
+        const float vx = s_v[(n * V + v) * 2], vy = s_v[(n * V + v) * 2 + 1];
+        lo_x = fminf(lo_x, vx); hi_x = fmaxf(hi_x, vx);
+        lo_y = fminf(lo_y, vy); hi_y = fmaxf(hi_y, vy);
+      }
+    }
+    p.cls[row] = c;
+    p.proj[row * 2] = valid ? __fmul_rn(p.down, s_m[2 * n]) : 0.f;
+    p.proj[row * 2 + 1] = valid ? __fmul_rn(p.down, s_m[2 * n + 1]) : 0.f;
+    p.bbox[row * 4 + 0] = lo_x; p.bbox[row * 4 + 1] = lo_y; p.bbox[row * 4 + 2] = hi_x; p.bbox[row * 4 + 3] = hi_y;
+  }
+}
+
+size_t post_fused_smem(int Cv, int K, int n_vert) {
+  return (static_cast<size_t>(Cv) * K * 2 + static_cast<size_t>(K) * n_vert * 2 + static_cast<size_t>(K) * 2) * sizeof(float);
+}
+
+int launch_post_fused(const PostFusedParams& p, int dtype, cudaStream_t s) {
+  const size_t smem = post_fused_smem(p.Cv, p.K, p.n_vert);
+  cudaError_t e;
+  if (dtype == 0) {
+    e = cudaFuncSetAttribute(post_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    post_fused_kernel<float><<<p.B, kPostThreads, smem, s>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(post_fused_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    post_fused_kernel<__nv_bfloat16><<<p.B, kPostThreads, smem, s>>>(p);
+  }
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // _group_vertexs_kf (models/model.py:134-162).  One CTA per image; thread per (detection n, channel k).
 //   rel  = v_kj - m_n                 (:147)      diff = rel - off_kn        (:149)
 //   dist = diff_x^2 + diff_y^2        (:150)      j*   = argmin_j, first minimal index (:151)

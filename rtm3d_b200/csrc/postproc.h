@@ -36,6 +36,19 @@ struct EpiKptParams {
 };
 int launch_epilogue_main(const EpiMainParams& p, int dtype, cudaStream_t s);
 int launch_epilogue_kpt(const EpiKptParams& p, int dtype, cudaStream_t s);
+// Everything after the selection of a fused decode in ONE kernel (one CTA per image): Tier B epilogue, Tier A epilogue
+// and the keypoint grouping.
+struct PostFusedParams {
+  const int32_t* flat; const int32_t* counts; const int32_t* kflat; const float* kscore;
+  const void* off; const void* off2; const void* voff2;
+  int B, C, Cv, H, W, n_vert, K;
+  float down;
+  int64_t* cls; float* proj; float* verts; float* bbox;      // Tier A
+  float* kxy;                                                 // Tier B candidates
+  float* kpt_proj; float* kpt_score; int32_t* kpt_j; float* verts_cv;   // grouping (verts_cv may be null)
+};
+size_t post_fused_smem(int Cv, int K, int n_vert);
+int launch_post_fused(const PostFusedParams& p, int dtype, cudaStream_t s);
 int launch_group(const GroupParams& p, int dtype, cudaStream_t s);
 int launch_box3d(const Box3dParams& p, int dtype, cudaStream_t s);
 int launch_sigmoid(const float* x, float* y, size_t n, cudaStream_t s);

@@ -224,8 +224,9 @@ class HeatmapDecoder:
         (PackedDetections, KeypointCandidates, GroupedKeypoints), all asynchronous.  ``fused`` (default): one call of
         ``rtm3d_decode_fused`` -- both heat-maps streamed by a single kernel launch, then the grouping kernel; otherwise
         the three separate entry points.  ``marks``: optional list that receives a recorded ``torch.cuda.Event`` before
-        the first and after every kernel (bench.py times the kernels with it; the fused call is then issued as
-        decode-without-grouping + ``rtm3d_group_vertices``, the same two launches with an event in between)."""
+        the plane-streaming kernel and after the epilogue and grouping kernels (bench.py times the kernels with it; the
+        fused call is then issued as selection-only ``rtm3d_decode_fused`` + ``rtm3d_post_fused``: the same two launches
+        with an event in between)."""
         def mark():
             if marks is not None:
                 e = torch.cuda.Event(enable_timing=True)
@@ -272,16 +273,18 @@ class HeatmapDecoder:
                 det.cls.data_ptr(), det.score.data_ptr(), det.proj.data_ptr(), det.verts.data_ptr(), det.bbox.data_ptr(),
                 det.flat.data_ptr(), det.counts.data_ptr(), cand.score.data_ptr(), cand.xy.data_ptr(), cand.flat.data_ptr(),
                 grp.kpt_proj.data_ptr(), grp.kpt_score.data_ptr(), grp.kpt_j.data_ptr(), grp.verts.data_ptr(),
-                ws.data_ptr(), ws.numel(), self.flags | (_native.FLAG_NO_GROUP if marks is not None else 0), stream)
+                ws.data_ptr(), ws.numel(),
+                self.flags | ((_native.FLAG_NO_GROUP | _native.FLAG_NO_EPILOGUE) if marks is not None else 0), stream)
             mark()
             _native.check(rc, "rtm3d_decode_fused")
             if marks is not None:
-                rc = self._lib.rtm3d_group_vertices(
-                    det.flat.data_ptr(), det.counts.data_ptr(), off.data_ptr(), off2.data_ptr(), dt, B, H, W, V, K,
-                    cand.score.data_ptr(), cand.xy.data_ptr(), Cv, self.down_sample, grp.kpt_proj.data_ptr(),
-                    grp.kpt_score.data_ptr(), grp.kpt_j.data_ptr(), grp.verts.data_ptr(), stream)
+                rc = self._lib.rtm3d_post_fused(
+                    det.flat.data_ptr(), det.counts.data_ptr(), cand.flat.data_ptr(), cand.score.data_ptr(),
+                    off.data_ptr(), off2.data_ptr(), voff2.data_ptr(), dt, B, C, Cv, H, W, V, K, self.down_sample,
+                    det.cls.data_ptr(), det.proj.data_ptr(), det.verts.data_ptr(), det.bbox.data_ptr(), cand.xy.data_ptr(),
+                    grp.kpt_proj.data_ptr(), grp.kpt_score.data_ptr(), grp.kpt_j.data_ptr(), grp.verts.data_ptr(), stream)
                 mark()
-                _native.check(rc, "rtm3d_group_vertices")
+                _native.check(rc, "rtm3d_post_fused")
         return det, cand, grp
 
     # ------------------------------------------------------------------ Tier C

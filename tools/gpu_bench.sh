@@ -14,6 +14,6 @@ python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/plain_$TAG.l
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches_$TAG.log 2>&1; echo "ncu launches rc=$?"
 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/plain2_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:decode_ -s 6 -c 2 -o gpurun_out/prof_$TAG -f \
+ncu --set full --clock-control none --import-source on -k regex:decode_planes -s 4 -c 1 -o gpurun_out/prof_$TAG -f \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
 fi
