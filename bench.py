@@ -58,6 +58,17 @@ def algorithmic_bytes_per_image(w, elem=4, n_vert=8):
     return main + kpt, main, kpt
 
 
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed ncu capture of
+    this workload (profiles/traffic.json, written by tools/summarise_profiles.py); None when there is none."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -176,7 +187,7 @@ def run_b200(args, w):
     import torch
     import torch.distributed as dist
     from rtm3d_b200 import HeatmapDecoder, HostDecodeSession
-    from rtm3d_b200.sharding import gather_detections
+    from rtm3d_b200.decoder import PackedDetections
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -196,7 +207,7 @@ def run_b200(args, w):
     sets = [make_inputs(torch, w, dev, 1234 + rank + 100 * s) for s in range(nsets)]
     heat_bytes = B * (w["C"] + Cv) * w["H"] * w["W"] * 4
     # kernels per step: plane-streaming kernel + fused post kernel (main only: + Tier A epilogue)
-    launches_per_step = 2
+    launches_per_step = 2 + (1 if world > 1 else 0)    # + the wire-packing kernel of the gather
     marks_per_step = 3 if Cv else 2          # events: before, after the plane kernel, after the post kernel
 
     gather_out = None
@@ -216,10 +227,11 @@ def run_b200(args, w):
             # the path's one collective: all-gather of the fixed-size detections, on the decode stream
             nonlocal gather_out
             if gather_out is None:
-                wire = det.to_wire()
-                gather_out = (torch.empty((world * B,) + tuple(wire.shape[1:]), dtype=wire.dtype, device=dev),
-                              torch.empty((world * B,), dtype=torch.int32, device=dev))
-            gather_detections(det, out=gather_out)
+                per = K * PackedDetections.WORDS + 1
+                gather_out = (torch.empty((world * B, per), dtype=torch.int32, device=dev),
+                              torch.empty((B, per), dtype=torch.int32, device=dev))
+            # pack (one launch of the library) + all-gather; the unpacked views are not materialised inside the step
+            dist.all_gather_into_tensor(gather_out[0], det.to_wire(gather_out[1]))
         return det, grp
 
     def barrier():
@@ -294,13 +306,13 @@ def run_b200(args, w):
                            l2=f"{nsets} input sets rotated, {heat_bytes / 1e6:.0f} MB of heat-map per step vs 126 MB L2"
                               + ("" if heat_bytes > 130e6 else " (SMALLER than L2: later steps may hit L2)")),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
                          "bytes_per_launch": dom_bytes, "kernel_ms": {k: round(v, 5) for k, v in kernel_ms.items()},
                          "step_achieved": round(step_gbs, 1), "step_frac": round(step_gbs / peak, 4),
                          "algorithmic_bytes_per_image": A},
             "e2e": {"value": round(B * world * e2e_steps / e2e_s, 1), "unit": UNIT, "h2d_bytes_per_step": sess.h2d_bytes(),
                     "d2h_bytes_per_step": sess.d2h_bytes(), "steps": e2e_steps,
-                    "api": "HostDecodeSession.run -> rtm3d_decode_main_host / rtm3d_decode_keypoints_host"},
+                    "api": "HostDecodeSession.run -> " + ("rtm3d_decode_fused_host" if Cv else "rtm3d_decode_main_host")},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": sampler.summary(t_wall0, t_wall1),
         }

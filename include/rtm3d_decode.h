@@ -142,6 +142,20 @@ int rtm3d_decode_fused(const void* hm, const void* off, const void* off2, const 
                        void* ws, size_t ws_bytes, unsigned flags, void* stream);
 
 /*
+ * rtm3d_decode_fused for HOST-resident head outputs: both heat-maps are copied to their device staging buffers
+ * (`dev_hm` B*C*H*W and `dev_kpt` B*Cv*H*W elements), the three regression maps must be page-locked mapped host memory
+ * and are read zero-copy (K*(2V+2) + Cv*K*2 scalars per image).  Results land in the device buffers; copying them back
+ * is left to the caller (one D2H per buffer on the same stream).
+ */
+int rtm3d_decode_fused_host(const void* hm_host, const void* off_host, const void* off2_host, const void* kpt_hm_host,
+                            const void* voff2_host, int dtype, int B, int C, int Cv, int H, int W, int n_vert, int K,
+                            float thresh, float down, void* dev_hm, void* dev_kpt,
+                            int64_t* cls, float* score, float* proj, float* verts, float* bbox, int32_t* flat, int32_t* counts,
+                            float* kscore, float* kxy, int32_t* kflat,
+                            float* kpt_proj, float* kpt_score, int32_t* kpt_j, float* verts_cv,
+                            void* ws, size_t ws_bytes, unsigned flags, void* stream);
+
+/*
  * Second halves of rtm3d_decode_main / rtm3d_decode_keypoints, enqueued by them unless RTM3D_FLAG_NO_EPILOGUE is set:
  *   rtm3d_epilogue_main       rows (flat, counts) -> cls, proj, verts, bbox: gather of offset_fr_main / main_offset at the
  *                             integer peak, sub-pixel add, vertex regress, x DOWN_SAMPLE, 2D box (models/model.py:47-50,
@@ -194,6 +208,14 @@ int rtm3d_decode_box3d(const int32_t* flat, const int32_t* counts, const void* r
                        int B, int C, int H, int W, int Creg, int K, int mode,
                        const float* cam, const float* dim_ref, float depth_mu, float depth_sigma,
                        float* loc, float* dim, float* alpha, float* rot_y, float* corners2d, void* stream);
+
+/*
+ * Packs the Tier A result of a batch into the wire rows of the multi-GPU gather (the path's one collective):
+ * wire int32 [B][K*(9+2*n_vert) + 1] = per image K rows of (cls | score | proj 2 | verts 2*n_vert | bbox 4 | flat) as
+ * 32-bit patterns, then counts[b].  One launch instead of a chain of torch cat / cast kernels.
+ */
+int rtm3d_pack_wire(const int64_t* cls, const float* score, const float* proj, const float* verts, const float* bbox,
+                    const int32_t* flat, const int32_t* counts, int B, int K, int n_vert, int32_t* wire, void* stream);
 
 /*
  * The library's sigmoid s(x) = 1.0f / (1.0f + expf(-x)) applied element-wise to n device floats: the function every

@@ -37,9 +37,12 @@ SIGNATURES = {
                            _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _u, _vp],
     "rtm3d_epilogue_main": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp],
     "rtm3d_epilogue_keypoints": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "rtm3d_decode_fused_host": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _vp,
+                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _u, _vp],
     "rtm3d_post_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f,
                          _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "rtm3d_group_vertices": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp],
+    "rtm3d_pack_wire": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],
     "rtm3d_sigmoid_f32": [_vp, _vp, _sz, _vp],
     "rtm3d_threshold_table": [_vp, _vp, _i, _c.POINTER(_i), _vp],
     "rtm3d_decode_box3d": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp],

@@ -327,6 +327,34 @@ int rtm3d_epilogue_keypoints(const int32_t* kflat, const void* voff2, int dtype,
   return cuda_fail(rtm3d::launch_epilogue_kpt(e, dtype, static_cast<cudaStream_t>(stream)), "Tier B epilogue launch");
 }
 
+int rtm3d_decode_fused_host(const void* hm_host, const void* off_host, const void* off2_host, const void* kpt_hm_host,
+                            const void* voff2_host, int dtype, int B, int C, int Cv, int H, int W, int n_vert, int K, float thresh,
+                            float down, void* dev_hm, void* dev_kpt, int64_t* cls, float* score, float* proj, float* verts,
+                            float* bbox, int32_t* flat, int32_t* counts, float* kscore, float* kxy, int32_t* kflat,
+                            float* kpt_proj, float* kpt_score, int32_t* kpt_j, float* verts_cv, void* ws, size_t ws_bytes,
+                            unsigned flags, void* stream) {
+  if (!hm_host || !off_host || !off2_host || !kpt_hm_host || !voff2_host || !dev_hm || !dev_kpt)
+    return fail(RTM3D_ERR_NULL, "NULL pointer argument");
+  if (dtype != RTM3D_F32 && dtype != RTM3D_BF16) return fail(RTM3D_ERR_DTYPE, "dtype %d", dtype);
+  if (int e = check_shape(B, C, H, W, K)) return e;
+  if (Cv < 1) return fail(RTM3D_ERR_SHAPE, "Cv=%d", Cv);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  void *d_off = nullptr, *d_off2 = nullptr, *d_voff2 = nullptr;
+  cudaError_t e = cudaHostGetDevicePointer(&d_off, const_cast<void*>(off_host), 0);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer(&d_off2, const_cast<void*>(off2_host), 0);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer(&d_voff2, const_cast<void*>(voff2_host), 0);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(static_cast<int>(e), "the regression maps must be page-locked mapped host memory: %s", cudaGetErrorString(e));
+  }
+  const size_t px = static_cast<size_t>(B) * H * W * elem_size(dtype);
+  if (int r = cuda_fail(static_cast<int>(cudaMemcpyAsync(dev_hm, hm_host, px * C, cudaMemcpyHostToDevice, s)), "H2D main heat-map")) return r;
+  if (int r = cuda_fail(static_cast<int>(cudaMemcpyAsync(dev_kpt, kpt_hm_host, px * Cv, cudaMemcpyHostToDevice, s)), "H2D keypoint heat-map")) return r;
+  return rtm3d_decode_fused(dev_hm, d_off, d_off2, dev_kpt, d_voff2, dtype, B, C, Cv, H, W, n_vert, K, thresh, down, cls, score, proj,
+                            verts, bbox, flat, counts, kscore, kxy, kflat, kpt_proj, kpt_score, kpt_j, verts_cv, ws, ws_bytes, flags,
+                            stream);
+}
+
 int rtm3d_post_fused(const int32_t* flat, const int32_t* counts, const int32_t* kflat, const float* kscore, const void* off,
                      const void* off2, const void* voff2, int dtype, int B, int C, int Cv, int H, int W, int n_vert, int K,
                      float down, int64_t* cls, float* proj, float* verts, float* bbox, float* kxy, float* kpt_proj,
@@ -369,6 +397,14 @@ int rtm3d_decode_box3d(const int32_t* flat, const int32_t* counts, const void* r
   if (Creg != (multibin ? 14 : 8)) return fail(RTM3D_ERR_SHAPE, "Creg=%d does not match mode %d (8 SMOKE-style, 14 multi-bin)", Creg, mode);
   rtm3d::Box3dParams q{flat, counts, reg, B, C, H, W, Creg, K, mode, cam, dim_ref, depth_mu, depth_sigma, loc, dim, alpha, rot_y, corners2d};
   return cuda_fail(rtm3d::launch_box3d(q, dtype, static_cast<cudaStream_t>(stream)), "box3d launch");
+}
+
+int rtm3d_pack_wire(const int64_t* cls, const float* score, const float* proj, const float* verts, const float* bbox,
+                    const int32_t* flat, const int32_t* counts, int B, int K, int n_vert, int32_t* wire, void* stream) {
+  if (!cls || !score || !proj || !verts || !bbox || !flat || !counts || !wire) return fail(RTM3D_ERR_NULL, "NULL pointer argument");
+  if (B < 1 || K < 1 || n_vert < 1 || n_vert > RTM3D_MAX_VERTS) return fail(RTM3D_ERR_SHAPE, "bad shape B=%d K=%d n_vert=%d", B, K, n_vert);
+  return cuda_fail(rtm3d::launch_pack_wire(cls, score, proj, verts, bbox, flat, counts, B, K, n_vert, wire,
+                                           static_cast<cudaStream_t>(stream)), "pack_wire launch");
 }
 
 int rtm3d_sigmoid_f32(const float* x, float* y, size_t n, void* stream) {

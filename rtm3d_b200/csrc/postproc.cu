@@ -388,6 +388,42 @@ __global__ void __launch_bounds__(128) box3d_kernel(const Box3dParams p) {
   for (int i = 0; i < 16; ++i) p.corners2d[row * 16 + i] = uv[i];
 }
 
+// Wire rows for the NCCL gather of the detections: per image K rows of (9 + 2V) 32-bit words
+// (cls | score | proj 2 | verts 2V | bbox 4 | flat) followed by one word holding counts[b].
+__global__ void __launch_bounds__(256) pack_wire_kernel(const int64_t* cls, const float* score, const float* proj, const float* verts,
+                                                        const float* bbox, const int32_t* flat, const int32_t* counts, int B, int K,
+                                                        int V, int32_t* wire) {
+  const int words = 9 + 2 * V;
+  const size_t per_img = static_cast<size_t>(K) * words + 1;
+  const size_t n = static_cast<size_t>(B) * per_img;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / per_img);
+    const int r = static_cast<int>(i - b * per_img);
+    int32_t v;
+    if (r == K * words) {
+      v = counts[b];
+    } else {
+      const int j = r / words, w = r - j * words;
+      const size_t row = static_cast<size_t>(b) * K + j;
+      if (w == 0) v = static_cast<int32_t>(cls[row]);
+      else if (w == 1) v = __float_as_int(score[row]);
+      else if (w < 4) v = __float_as_int(proj[row * 2 + (w - 2)]);
+      else if (w < 4 + 2 * V) v = __float_as_int(verts[row * 2 * V + (w - 4)]);
+      else if (w < 8 + 2 * V) v = __float_as_int(bbox[row * 4 + (w - 4 - 2 * V)]);
+      else v = flat[row];
+    }
+    wire[i] = v;
+  }
+}
+int launch_pack_wire(const int64_t* cls, const float* score, const float* proj, const float* verts, const float* bbox,
+                     const int32_t* flat, const int32_t* counts, int B, int K, int V, int32_t* wire, cudaStream_t s) {
+  const size_t n = static_cast<size_t>(B) * (static_cast<size_t>(K) * (9 + 2 * V) + 1);
+  unsigned grid = static_cast<unsigned>((n + 255) / 256);
+  if (grid > 148u * 16u) grid = 148u * 16u;
+  pack_wire_kernel<<<grid, 256, 0, s>>>(cls, score, proj, verts, bbox, flat, counts, B, K, V, wire);
+  return static_cast<int>(cudaGetLastError());
+}
+
 // The library's sigmoid, element-wise (verification aid: tests sweep every fp32 value through it).
 __global__ void sigmoid_kernel(const float* x, float* y, size_t n) {
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)

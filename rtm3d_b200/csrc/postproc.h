@@ -51,6 +51,8 @@ size_t post_fused_smem(int Cv, int K, int n_vert);
 int launch_post_fused(const PostFusedParams& p, int dtype, cudaStream_t s);
 int launch_group(const GroupParams& p, int dtype, cudaStream_t s);
 int launch_box3d(const Box3dParams& p, int dtype, cudaStream_t s);
+int launch_pack_wire(const int64_t* cls, const float* score, const float* proj, const float* verts, const float* bbox,
+                     const int32_t* flat, const int32_t* counts, int B, int K, int V, int32_t* wire, cudaStream_t s);
 int launch_sigmoid(const float* x, float* y, size_t n, cudaStream_t s);
 
 }  // namespace rtm3d

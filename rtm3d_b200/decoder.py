@@ -32,25 +32,42 @@ class PackedDetections:
     flat: torch.Tensor     # int32 [B,K]     c*H*W + y*W + x of the peak
     counts: torch.Tensor   # int32 [B]
 
-    WORDS = 1 + 1 + 2 + 16 + 4 + 1  # per-detection 32-bit words of the wire format used by the NCCL gather
+    WORDS = 1 + 1 + 2 + 16 + 4 + 1  # per-detection 32-bit words of the wire format used by the NCCL gather (V = 8)
 
-    def to_wire(self) -> torch.Tensor:
-        """[B,K,W] int32 bit-pattern tensor (cls as i32 | score | proj | verts | bbox | flat) for a single collective."""
+    def to_wire(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """int32 [B, K*(9+2V)+1]: per image K rows of (cls | score | proj | verts | bbox | flat) as bit patterns, then the
+        image's count -- ONE buffer for ONE collective.  CUDA tensors are packed by the library (rtm3d_pack_wire, one
+        launch); CPU tensors (the gloo tests) by torch."""
         B, K = self.score.shape
+        V = self.verts.shape[2]
+        per = K * (9 + 2 * V) + 1
+        if out is None:
+            out = torch.empty((B, per), dtype=torch.int32, device=self.score.device)
+        if self.score.is_cuda:
+            with torch.cuda.device(self.score.device):
+                _native.check(_native.lib().rtm3d_pack_wire(
+                    self.cls.data_ptr(), self.score.data_ptr(), self.proj.data_ptr(), self.verts.data_ptr(), self.bbox.data_ptr(),
+                    self.flat.data_ptr(), self.counts.data_ptr(), B, K, V, out.data_ptr(),
+                    torch.cuda.current_stream(self.score.device).cuda_stream), "rtm3d_pack_wire")
+            return out
         parts = [self.cls.to(torch.int32).view(B, K, 1), self.score.view(torch.int32).view(B, K, 1),
                  self.proj.view(torch.int32).view(B, K, 2), self.verts.reshape(B, K, -1).view(torch.int32),
                  self.bbox.view(torch.int32).view(B, K, 4), self.flat.view(B, K, 1)]
-        return torch.cat(parts, dim=-1)
+        out[:, :per - 1] = torch.cat(parts, dim=-1).reshape(B, per - 1)
+        out[:, per - 1] = self.counts
+        return out
 
     @staticmethod
-    def from_wire(wire: torch.Tensor, counts: torch.Tensor) -> "PackedDetections":
-        B, K, Wd = wire.shape
+    def from_wire(wire: torch.Tensor, K: int) -> "PackedDetections":
+        B, per = wire.shape
+        Wd = (per - 1) // K
         V = (Wd - 9) // 2
-        f = wire.view(torch.float32)
-        return PackedDetections(cls=wire[..., 0].to(torch.int64), score=f[..., 1].contiguous(),
+        rows = wire[:, :per - 1].reshape(B, K, Wd)
+        f = rows.view(torch.float32)
+        return PackedDetections(cls=rows[..., 0].to(torch.int64), score=f[..., 1].contiguous(),
                                 proj=f[..., 2:4].contiguous(), verts=f[..., 4:4 + 2 * V].reshape(B, K, V, 2).contiguous(),
-                                bbox=f[..., 4 + 2 * V:8 + 2 * V].contiguous(), flat=wire[..., 8 + 2 * V].contiguous(),
-                                counts=counts)
+                                bbox=f[..., 4 + 2 * V:8 + 2 * V].contiguous(), flat=rows[..., 8 + 2 * V].contiguous(),
+                                counts=wire[:, per - 1].contiguous())
 
 
 @dataclass
@@ -317,7 +334,8 @@ class HeatmapDecoder:
 
 class HostDecodeSession:
     """End-to-end path for HOST-resident head outputs (what a caller outside the training process has): page-locked
-    host tensors in, page-locked host tensors out, through ``rtm3d_decode_main_host`` / ``rtm3d_decode_keypoints_host``.
+    host tensors in, page-locked host tensors out, through ``rtm3d_decode_fused_host`` (main + keypoint branch) or
+    ``rtm3d_decode_main_host`` (main branch only).
 
     Per step the heat-maps (main, and the keypoint heat-map when given) cross PCIe once; the regression maps stay in
     host memory and only the K*(2V+2) (+ Cv*K*2) scalars the decode needs are read from them by the GPU (zero-copy).
@@ -366,6 +384,8 @@ class HostDecodeSession:
         for t in (main, off, off2, voff2) + ((kpt_host,) if kpt_host is not None else ()):
             if t.is_cuda or not t.is_pinned() or not t.is_contiguous():
                 raise ValueError("HostDecodeSession.run expects contiguous page-locked host tensors")
+        if kpt_host is not None:
+            return self._run_fused(pred_logits_host, kpt_host, sync)
         dt = _dtype_code(main)
         with torch.cuda.device(self.dev):
             ws, stream = dec._workspace(self.dev, B, C, H, W)
@@ -377,23 +397,31 @@ class HostDecodeSession:
                 ph.cls.data_ptr(), ph.score.data_ptr(), ph.proj.data_ptr(), ph.verts.data_ptr(), ph.bbox.data_ptr(),
                 ph.flat.data_ptr(), ph.counts.data_ptr(), ws.data_ptr(), ws.numel(), dec.flags, stream),
                 "rtm3d_decode_main_host")
-            if kpt_host is not None:
-                Cv = self.Cv
-                ws2, _ = dec._workspace(self.dev, B, Cv, H, W)
-                c = self.cand
-                _native.check(lib.rtm3d_decode_keypoints_host(
-                    kpt_host.data_ptr(), voff2.data_ptr(), dt, B, Cv, H, W, K, self.dev_kpt.data_ptr(),
-                    c.score.data_ptr(), c.xy.data_ptr(), c.flat.data_ptr(), None, None, None,
-                    ws2.data_ptr(), ws2.numel(), dec.flags, stream), "rtm3d_decode_keypoints_host")
-                g, gh = self.grp, self.grp_host
-                # pinned host memory is mapped into the device address space (UVA): the grouping kernel re-reads the
-                # K*(2V+2) regression scalars straight from host memory
-                _native.check(lib.rtm3d_group_vertices(
-                    p.flat.data_ptr(), p.counts.data_ptr(), off.data_ptr(), off2.data_ptr(), dt, B, H, W, V, K,
-                    c.score.data_ptr(), c.xy.data_ptr(), Cv, dec.down_sample, g.kpt_proj.data_ptr(), g.kpt_score.data_ptr(),
-                    g.kpt_j.data_ptr(), g.verts.data_ptr(), stream), "rtm3d_group_vertices")
-                for name in ("kpt_proj", "kpt_score", "kpt_j", "verts"):
-                    getattr(gh, name).copy_(getattr(g, name), non_blocking=True)
+            if sync:
+                torch.cuda.current_stream(self.dev).synchronize()
+        return self.det_host, self.grp_host
+
+    def _run_fused(self, pred_logits_host, kpt_host, sync):
+        """Main + keypoint branch: rtm3d_decode_fused_host (two H2D copies, one streaming launch, one post kernel), D2H."""
+        dec, lib = self.dec, self.dec._lib
+        B, C, H, W = self.shape
+        K, V, Cv = dec.topk, self.V, self.Cv
+        main, off, off2, voff2 = pred_logits_host
+        dt = _dtype_code(main)
+        with torch.cuda.device(self.dev):
+            ws, stream = dec._workspace(self.dev, B, C + Cv, H, W)
+            p, c, g = self.det, self.cand, self.grp
+            _native.check(lib.rtm3d_decode_fused_host(
+                main.data_ptr(), off.data_ptr(), off2.data_ptr(), kpt_host.data_ptr(), voff2.data_ptr(), dt, B, C, Cv, H, W, V, K,
+                dec.score_thresh, dec.down_sample, self.dev_hm.data_ptr(), self.dev_kpt.data_ptr(),
+                p.cls.data_ptr(), p.score.data_ptr(), p.proj.data_ptr(), p.verts.data_ptr(), p.bbox.data_ptr(), p.flat.data_ptr(),
+                p.counts.data_ptr(), c.score.data_ptr(), c.xy.data_ptr(), c.flat.data_ptr(),
+                g.kpt_proj.data_ptr(), g.kpt_score.data_ptr(), g.kpt_j.data_ptr(), g.verts.data_ptr(),
+                ws.data_ptr(), ws.numel(), dec.flags, stream), "rtm3d_decode_fused_host")
+            for name in ("cls", "score", "proj", "verts", "bbox", "flat", "counts"):
+                getattr(self.det_host, name).copy_(getattr(p, name), non_blocking=True)
+            for name in ("kpt_proj", "kpt_score", "kpt_j", "verts"):
+                getattr(self.grp_host, name).copy_(getattr(g, name), non_blocking=True)
             if sync:
                 torch.cuda.current_stream(self.dev).synchronize()
         return self.det_host, self.grp_host

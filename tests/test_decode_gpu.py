@@ -224,3 +224,18 @@ def test_speculative_start_threshold_is_exact(max_ctas, speculate):
     # the workspace is left clean: a second run gives the same result
     again = dec.decode_packed(dev_logits)
     assert torch.equal(again.flat, packed.flat) and torch.equal(again.score, packed.score)
+
+
+def test_pack_wire_kernel_matches_torch_packing():
+    """rtm3d_pack_wire (the gather's wire rows, one launch) == the torch cat/cast chain, bit for bit."""
+    from rtm3d_b200.decoder import PackedDetections
+    logits, _ = synth.head_outputs(3, 3, 48, 80, seed=33, kind="randn")
+    dec = HeatmapDecoder(0.4, 30, 4.0)
+    det = dec.decode_packed([t.to(DEV) for t in logits])
+    torch.cuda.synchronize()
+    wire = det.to_wire()
+    cpu = PackedDetections(**{f: getattr(det, f).cpu() for f in ("cls", "score", "proj", "verts", "bbox", "flat", "counts")})
+    assert torch.equal(wire.cpu(), cpu.to_wire())
+    back = PackedDetections.from_wire(wire, 30)
+    for f in ("cls", "score", "proj", "verts", "bbox", "flat", "counts"):
+        assert torch.equal(getattr(back, f), getattr(det, f)), f

@@ -110,3 +110,23 @@ def test_keypoint_branch_vs_golden(name):
         assert same.mean() > 0.98, f"{name} image {b}: only {same.mean():.3f} of matched keypoints agree"
         sc_ok = np.isclose(grp.kpt_score[b, :n].cpu().numpy(), want["kpt_score"], rtol=1e-4, atol=1e-6)[:, clean]
         assert sc_ok[same].all()
+
+
+def test_host_session_matches_device_path():
+    """End-to-end entry points (pinned host in, pinned host out; regression maps read zero-copy) give the device path's bits."""
+    from rtm3d_b200 import HostDecodeSession
+    B, C, Cv, H, W, K = 3, 3, 9, 48, 80, 30
+    logits, kpt = synth.head_outputs(B, C, H, W, seed=91, kind="randn", kpt_channels=Cv)
+    dec = HeatmapDecoder(0.4, K, 4.0)
+    det, cand, grp = dec.decode_with_keypoints([t.to(DEV) for t in logits], kpt.to(DEV))
+    host = [t.pin_memory() for t in logits]
+    sess = HostDecodeSession(dec, B, C, H, W, n_vert=8, kpt_channels=Cv, device=DEV)
+    det_h, grp_h = sess.run(host, kpt.pin_memory(), sync=True)
+    for f in ("cls", "score", "proj", "verts", "bbox", "flat", "counts"):
+        assert torch.equal(getattr(det, f).cpu(), getattr(det_h, f)), f
+    for f in ("kpt_proj", "kpt_score", "kpt_j", "verts"):
+        assert torch.equal(getattr(grp, f).cpu(), getattr(grp_h, f)), f
+    main_only = HostDecodeSession(dec, B, C, H, W, n_vert=8, device=DEV)
+    det_m, _ = main_only.run(host, None, sync=True)
+    for f in ("cls", "score", "proj", "verts", "bbox", "flat", "counts"):
+        assert torch.equal(getattr(det, f).cpu(), getattr(det_m, f)), f

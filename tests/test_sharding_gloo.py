@@ -43,10 +43,10 @@ def test_shard_range_partitions_the_batch():
 
 def test_wire_roundtrip_is_bit_exact():
     det = _fake_detections(5, 20, 8, seed=3)
-    back = PackedDetections.from_wire(det.to_wire(), det.counts)
+    back = PackedDetections.from_wire(det.to_wire(), 20)
     for f in ("cls", "score", "proj", "verts", "bbox", "flat", "counts"):
         assert torch.equal(getattr(det, f), getattr(back, f)), f
-    assert det.to_wire().shape[-1] == PackedDetections.WORDS == 25
+    assert det.to_wire().shape[-1] == 20 * PackedDetections.WORDS + 1 and PackedDetections.WORDS == 25
 
 
 def _worker(rank, world, port, B, K, V, q):

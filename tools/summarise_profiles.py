@@ -71,3 +71,21 @@ with open(os.path.join(pr, f"{tag}_bench.jsonl"), "w") as f:
         for line in open(p):
             if line.strip().startswith("{"):
                 f.write(line)
+
+# dram traffic of the plane-streaming kernel per launch -> profiles/traffic.json (bench.py reports it as roofline.traffic)
+if os.path.exists(rep):
+    import json
+    tr = {}
+    for r in rows[2:]:
+        if "decode_planes" in r[h.index("Kernel Name")]:
+            rd, wr = r[h.index("dram__bytes_read.sum")], r[h.index("dram__bytes_write.sum")]
+            unit_r, unit_w = rows[1][h.index("dram__bytes_read.sum")], rows[1][h.index("dram__bytes_write.sum")]
+            scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            tr = {"bytes": int(float(rd.replace(",", "")) * scale[unit_r] + float(wr.replace(",", "")) * scale[unit_w]),
+                  "source": f"profiles/{tag}_ncu_full.txt (ncu --set full, one launch of decode_planes_kernel, default bench workload cfg4)"}
+    if tr:
+        path = os.path.join(pr, "traffic.json")
+        cur = json.load(open(path)) if os.path.exists(path) else {}
+        cur["cfg4"] = tr
+        json.dump(cur, open(path, "w"), indent=1)
+        print("traffic", tr)
