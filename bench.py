@@ -198,7 +198,12 @@ def run_b200(args, w):
         raise SystemExit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch N>1 with torch.distributed.run")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    saved_stdout = None
     if world > 1:
+        # NCCL writes its version banner to stdout on the first communicator: keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     K, B, Cv = w["K"], w["B"], w["kpt"]
@@ -224,14 +229,22 @@ def run_b200(args, w):
                 e = torch.cuda.Event(enable_timing=True); e.record(); marks.append(e)
             grp = None
         if world > 1:
-            # the path's one collective: all-gather of the fixed-size detections, on the decode stream
+            # the path's one collective: pack (one launch of the library) + all-gather of the fixed-size
+            # detections.  It runs on a second stream behind an event, so the gather of batch i overlaps the decode of
+            # batch i+1; the timed region ends with a device-wide synchronise, i.e. with every gather complete.
             nonlocal gather_out
             if gather_out is None:
                 per = K * PackedDetections.WORDS + 1
-                gather_out = (torch.empty((world * B, per), dtype=torch.int32, device=dev),
-                              torch.empty((B, per), dtype=torch.int32, device=dev))
-            # pack (one launch of the library) + all-gather; the unpacked views are not materialised inside the step
-            dist.all_gather_into_tensor(gather_out[0], det.to_wire(gather_out[1]))
+                gather_out = dict(stream=torch.cuda.Stream(device=dev), keep=[None, None],
+                                  full=[torch.empty((world * B, per), dtype=torch.int32, device=dev) for _ in range(2)],
+                                  mine=[torch.empty((B, per), dtype=torch.int32, device=dev) for _ in range(2)])
+            slot = i & 1
+            ready = torch.cuda.Event()
+            ready.record()
+            with torch.cuda.stream(gather_out["stream"]):
+                gather_out["stream"].wait_event(ready)
+                dist.all_gather_into_tensor(gather_out["full"][slot], det.to_wire(gather_out["mine"][slot]))
+            gather_out["keep"][slot] = det          # the result buffers stay referenced until their gather has been issued twice over
         return det, grp
 
     def barrier():
@@ -321,6 +334,9 @@ def run_b200(args, w):
             line["cpu_baseline"] = {"value": round(ips, 2), "unit": UNIT, "cores": cores, "kind": "port", "torch_threads": threads,
                                     "sample": f"{nb} images of the workload, 1 warm-up + 3 timed passes of the torch port of "
                                               "Model.inference (incl. the clone of models/model.py:27 and the keypoint branch)"}
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
