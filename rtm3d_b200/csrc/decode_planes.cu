@@ -60,7 +60,7 @@ constexpr int kScoreShift = 17;
 constexpr uint32_t kScoreBase = 0x33800000u >> kScoreShift; // bits of 2^-24
 constexpr int kMaxStages = 4;
 constexpr int kMaxPlanes = 64;           // plane indices with a remembered threshold (speculation)
-constexpr int kSpecMargin = 2;           // bins below the remembered boundary the speculative threshold starts at
+constexpr int kSpecMargin = 1;           // bins below the remembered boundary the speculative threshold starts at
 constexpr int kUpdateEvery = 48;         // appended keys between two threshold updates
 
 struct PlaneGeom {
@@ -68,6 +68,7 @@ struct PlaneGeom {
   int stage_shift;    // log2(stages)
   int speculate;      // 1: start items at the threshold remembered from the previous item of the same plane index
   int chunk_rows;     // centre rows per chunk
+  int copy_rows;      // rows per bulk copy (a chunk = ceil((chunk_rows + 2) / copy_rows) copies on one barrier)
   int stage_bytes;    // (chunk_rows + 2) * row_bytes
   int row_bytes;
   int gpr;            // 16-byte groups per row
@@ -674,7 +675,14 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
             ctl.wl_next[s] = 0u;                        // every B-warp has left the stage (empty) / nobody has entered it yet
             RTM3D_TRACE(8);
             pl::mbar_arrive_expect_tx(bar, bytes);
-            pl::bulk_g2s(dst, it.base + static_cast<size_t>(pli) * it.plane_bytes + static_cast<size_t>(top) * g.row_bytes, bytes, bar);
+            {
+              // the chunk goes out as a few bulk copies on one barrier: several copies in flight per stage keep the
+              // copy engine's request stream dense
+              const unsigned char* src = it.base + static_cast<size_t>(pli) * it.plane_bytes + static_cast<size_t>(top) * g.row_bytes;
+              const uint32_t piece = static_cast<uint32_t>(g.copy_rows) * g.row_bytes;
+              for (uint32_t o2 = 0; o2 < bytes; o2 += piece)
+                pl::bulk_g2s(dst + o2, src + o2, min(piece, bytes - o2), bar);
+            }
             if (++qq == it.cpp) { qq = 0; ++pli; }
           }
         }
@@ -806,11 +814,17 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
           for (int a = 0; a < kAWarps; ++a) { n += static_cast<int>(ctl.wl_count[s][a]); seg_end[a] = n; }
           const int nb_batches = (g.debug == 1 || g.debug == 3 || g.debug == 7) ? 0 : ((n + 31) >> 5);
           if (warp == kBWarp0 && lane == 0) RTM3D_ACC(kStWlEntries, n);
-          while (true) {
-            int bt = 0;
-            if (lane == 0) bt = static_cast<int>(atomicAdd(&ctl.wl_next[s], 1u));
-            bt = __shfl_sync(0xffffffffu, bt, 0);
-            if (bt >= nb_batches) break;
+          // Batches are handed out by a shared counter.  The stage is only needed for a batch's loads: the next batch is
+          // claimed right after them, and when there is none the stage goes back to the producer BEFORE this warp works
+          // through its candidates (sigmoid, list append, threshold update).
+          auto grab = [&]() {
+            int b2 = 0;
+            if (lane == 0) b2 = static_cast<int>(atomicAdd(&ctl.wl_next[s], 1u));
+            return __shfl_sync(0xffffffffu, b2, 0);
+          };
+          bool released = false;
+          int bt = grab();
+          while (bt < nb_batches) {
             const int wi = bt * 32 + lane;
             uint32_t pm = 0;                 // pixels of this lane's group that may be candidates
             float v[E], nb[E];
@@ -833,7 +847,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
               c4 = gi - rl * gpr;                                                                   // group within the row
               y = c_lo + rl;
             }
-            if (!__any_sync(0xffffffffu, alive)) continue;
+            if (!__any_sync(0xffffffffu, alive)) { bt = grab(); continue; }
             if (lane == 0) RTM3D_ACC(kStBatches, 1);
             if (alive) {
               const bool has_up = y > 0, has_dn = y + 1 < H, has_l = c4 > 0, has_r = c4 + 1 < gpr;
@@ -854,6 +868,12 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
                 const bool dead = (xc <= kSatKnee && xc >= kDenormKnee && nb[i] > xc + kTieTol);
                 if (xc >= tf && !dead) pm |= 1u << i;
               }
+            }
+            bt = grab();
+            if (bt >= nb_batches && !released) {
+              __syncwarp();
+              if (lane == 0) pl::mbar_arrive(pl::smem_u32(&ctl.empty[s]));
+              released = true;
             }
             // per-lane candidate loop; a lane that finds the list full parks (`stuck`) until the warp has made room
             while (__any_sync(0xffffffffu, pm != 0u)) {
@@ -917,7 +937,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
             }
           }
           __syncwarp();
-          if (lane == 0) pl::mbar_arrive(pl::smem_u32(&ctl.empty[s]));
+          if (!released && lane == 0) pl::mbar_arrive(pl::smem_u32(&ctl.empty[s]));
           if (q == it.nchunks - 1) {
             // the last B-warp to leave the item brings the histogram boundary up to date for the finisher
             int last = 0;
@@ -1154,6 +1174,8 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
 // ---------------------------------------------------------------------------------------------------------------
 static int g_sm_count = 0;
 static unsigned long long* g_stats = nullptr;
+static int g_copy_rows = 0;   // developer knob (debug_set_copy_rows): rows per bulk copy, 0 = whole chunk
+void debug_set_copy_rows(int r) { g_copy_rows = r; }
 void debug_set_stats(unsigned long long* dev_u64_16) { g_stats = dev_u64_16; }
 
 static bool make_plane_geom(const PlaneParams& p, int dtype, int split_override, int speculate, PlaneGeom& g) {
@@ -1231,6 +1253,7 @@ static bool make_plane_geom(const PlaneParams& p, int dtype, int split_override,
   g.stage_shift = stages == 4 ? 2 : 1;
   g.speculate = speculate;
   g.chunk_rows = cr;
+  g.copy_rows = g_copy_rows > 0 ? g_copy_rows : cr + 2;
   g.stage_bytes = (cr + 2) * row_bytes;
   {
     const int tasks = (cr * g.gpr + 31) / 32;                             // tasks of 32 groups in a chunk

@@ -70,7 +70,8 @@ int launch_planes(const PlaneParams& p, int dtype, int split_override, int specu
 bool planes_eligible(const PlaneParams& p, int dtype);
 constexpr int kPlanesMaxSplit = 8;
 int threshold_table_bins();
-void debug_set_stats(unsigned long long* dev_u64_16);   // developer instrumentation, not part of the public ABI
+void debug_set_stats(unsigned long long* dev_u64_16);
+void debug_set_copy_rows(int rows);   // developer instrumentation, not part of the public ABI
 int launch_threshold_table(float* t, uint32_t* edge, cudaStream_t s);
 
 }  // namespace rtm3d
