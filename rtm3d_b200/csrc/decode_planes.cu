@@ -159,9 +159,10 @@ struct __align__(16) Sel {
   volatile float t_filter;      // running logit threshold
   volatile unsigned long long kstar;  // exact key bound after a compaction (0 = none)
   volatile int spec_bin;        // speculative start threshold of the item (histogram bin, -1 = none); set by the finisher
+  volatile float spec_t;        // its logit bound filter_from_bin(spec_bin) (-inf when none), computed once per item
   volatile int last_bin;        // histogram boundary at the last threshold update (-1: fewer than K keys so far)
   uint32_t b_done;              // B-warps that have finished the item's last chunk
-  uint32_t pad[3];
+  uint32_t pad[2];
 };
 
 struct __align__(16) PlaneCtl {
@@ -590,7 +591,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
       pl::mbar_init(pl::smem_u32(&ctl.item_done[q]), kBWarps);
       pl::mbar_init(pl::smem_u32(&ctl.buf_free[q]), 1);
       Sel& L = ctl.sel[q];
-      L.reserve = 0; L.lock = 0; L.last_upd = 0; L.t_filter = -INFINITY; L.kstar = 0ull; L.spec_bin = -1;
+      L.reserve = 0; L.lock = 0; L.last_upd = 0; L.t_filter = -INFINITY; L.kstar = 0ull; L.spec_bin = -1; L.spec_t = -INFINITY;
       L.last_bin = -1; L.b_done = 0;
       ctl.fin_released[q] = 0u;
     }
@@ -626,7 +627,11 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
     // the first items of this CTA start from what the previous launch remembered
     for (int q = 0; q < kNBuf; ++q) {
       const long long item = static_cast<long long>(blockIdx.x) + static_cast<long long>(q) * gridDim.x;
-      if (item < g.n_items) ctl.sel[q].spec_bin = spec_for_plane(plane_of_slot(static_cast<int>((item % per_img) >> g.split_shift)));
+      if (item < g.n_items) {
+        const int sb = spec_for_plane(plane_of_slot(static_cast<int>((item % per_img) >> g.split_shift)));
+        ctl.sel[q].spec_bin = sb;
+        ctl.sel[q].spec_t = filter_from_bin(sb);
+      }
     }
   }
   __syncthreads();
@@ -662,7 +667,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
             const uint32_t s = gq & smask;
             if (gq >= static_cast<uint32_t>(S)) {
               const long long w0 = RTM3D_CLK();
-              pl::mbar_wait(pl::smem_u32(&ctl.empty[s]), ((gq >> sshift) - 1u) & 1u, p.status, 0xE1000001u, 32);
+              pl::mbar_wait(pl::smem_u32(&ctl.empty[s]), ((gq >> sshift) - 1u) & 1u, p.status, 0xE1000001u, 64);
               RTM3D_ACC(kStProdWait, RTM3D_CLK() - w0);
             }
             const int c_lo = it.ys + qq * g.chunk_rows, c_hi = min(c_lo + g.chunk_rows, it.ye);
@@ -707,17 +712,14 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
         // start threshold: the score threshold's logit (main planes) and, speculatively, a few bins below where the
         // previous item of the same plane index ended (verified by the finisher; a miss is redone in pass 1)
         float t_floor = it.is_main ? p.t0 : -INFINITY;
-        {
-          const int sb = L.spec_bin;
-          if (sb >= 1) t_floor = fmaxf(t_floor, filter_from_bin(sb));
-        }
+        t_floor = fmaxf(t_floor, L.spec_t);
         if (lane == 0) RTM3D_ACC(kStASetup, RTM3D_CLK() - as0);
         int qq = 0;                                     // chunk within the plane
         for (int q = 0; q < it.nchunks; ++q, ++gq) {
           const uint32_t s = gq & smask;
           {
             const long long w0 = RTM3D_CLK();
-            pl::mbar_wait(pl::smem_u32(&ctl.full[s]), (gq >> sshift) & 1u, p.status, 0xE1000002u, 32);
+            pl::mbar_wait(pl::smem_u32(&ctl.full[s]), (gq >> sshift) & 1u, p.status, 0xE1000002u, 100);
             if (lane == 0) RTM3D_ACC(kStWaitFull, RTM3D_CLK() - w0);
           }
           const long long al0 = RTM3D_CLK();
@@ -788,17 +790,14 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
         unsigned long long* list = list_all + static_cast<size_t>(buf) * g.list_cap;
         const float lim = it.is_main ? p.thresh : 0.0f;      // strict: score > lim (models/model.py:91; 0.0 = filler)
         float t_floor = it.is_main ? p.t0 : -INFINITY;
-        {
-          const int sb = L.spec_bin;
-          if (sb >= 1) t_floor = fmaxf(t_floor, filter_from_bin(sb));
-        }
+        t_floor = fmaxf(t_floor, L.spec_t);
         int qq = 0;                                     // chunk within the plane
         uint32_t flat_base = it.flat_base;              // of the plane the chunk belongs to
         for (int q = 0; q < it.nchunks; ++q, ++gq) {
           const uint32_t s = gq & smask;
           {
             const long long w0 = RTM3D_CLK();
-            pl::mbar_wait(pl::smem_u32(&ctl.scanned[s]), (gq >> sshift) & 1u, p.status, 0xE1000005u, 32);
+            pl::mbar_wait(pl::smem_u32(&ctl.scanned[s]), (gq >> sshift) & 1u, p.status, 0xE1000005u, 100);
             if (lane == 0) RTM3D_ACC(kStWaitScanned, RTM3D_CLK() - w0);
           }
           const long long bb0 = RTM3D_CLK();
@@ -978,8 +977,8 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
         const long long f0 = RTM3D_CLK();
         // the previous use of this buffer must have been taken over by its finisher before this use's barrier phase can
         // be waited for by parity
-        while (ctl.fin_released[buf] != (ord >> kBufShift)) __nanosleep(100);
-        pl::mbar_wait(pl::smem_u32(&ctl.item_done[buf]), (ord >> kBufShift) & 1u, p.status, 0xE1000004u, 64);
+        while (ctl.fin_released[buf] != (ord >> kBufShift)) __nanosleep(200);
+        pl::mbar_wait(pl::smem_u32(&ctl.item_done[buf]), (ord >> kBufShift) & 1u, p.status, 0xE1000004u, 200);
         const long long f1 = RTM3D_CLK();
         long long lap_ = f1;
         (void)lap_;
@@ -1049,6 +1048,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
             nsb = spec_for_plane(plane_of_slot(rn >> g.split_shift));
           }
           L.spec_bin = nsb;
+          L.spec_t = filter_from_bin(nsb);          // (-inf for nsb < 1)
           __threadfence_block();
           ctl.fin_released[buf] = (ord >> kBufShift) + 1u;
           pl::mbar_arrive(pl::smem_u32(&ctl.buf_free[buf]));
