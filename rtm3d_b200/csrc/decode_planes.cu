@@ -43,6 +43,9 @@
 namespace rtm3d {
 
 constexpr int kAWarps = 8;               // threshold-filter warps (phase A), two per SM sub-partition
+constexpr int kAGroups = 2;              // A-warp groups: group g scans the chunks with (chunk number % kAGroups) == g, so that
+                                         // kAGroups chunks are being filtered at any time
+constexpr int kAPerGroup = kAWarps / kAGroups;
 constexpr int kBWarps = 7;               // peak-test / candidate warps (phase B)
 constexpr int kFinWarps = 4;              // each finishes whole items on its own (ticket order)
 // Warp ids: finishers 0..3, B-warps 4..10, producer 11, A-warps 12..19 (two A-warps per SM sub-partition).  The order of
@@ -78,7 +81,7 @@ struct PlaneGeom {
   int rows_lo, nch_lo, nch_hi;  // rows of the shorter strips and chunks per strip (shorter / longer strips)
   int list_cap;       // keys per candidate list
   int fin_cap;        // keys per finisher buffer (two per finisher warp)
-  int wl_cap;         // worklist entries per stage (kAWarps segments)
+  int wl_cap;         // worklist entries per stage (kAPerGroup segments)
   int wl_seg;         // worklist entries per A-warp segment (= the groups one A-warp scans in a chunk, rounded up)
   int n_items;
   int max_ctas;       // 0 = one CTA per SM
@@ -172,7 +175,7 @@ struct __align__(16) PlaneCtl {
   unsigned long long item_done[kNBuf];
   unsigned long long buf_free[kNBuf];
   Sel sel[kNBuf];
-  volatile uint32_t wl_count[kMaxStages][kAWarps];   // worklist entries per stage and A-warp (written by that A-warp after its scan)
+  volatile uint32_t wl_count[kMaxStages][kAPerGroup];   // worklist entries per stage and A-warp (written by that A-warp after its scan)
   uint32_t wl_next[kMaxStages];             // next batch of the stage's worklist to hand out (reset with wl_count)
   uint32_t rsel[kNBuf + kFinWarps][264];   // radix-select scratch: [buf] B-warp compaction of that buffer, [kNBuf + w] finisher warp w
   uint32_t fin_next;            // next item ordinal to hand to a finisher warp
@@ -583,8 +586,8 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
     sp = p;
     for (int s = 0; s < S; ++s) {
       pl::mbar_init(pl::smem_u32(&ctl.full[s]), 1);
-      pl::mbar_init(pl::smem_u32(&ctl.scanned[s]), kAWarps);
-      pl::mbar_init(pl::smem_u32(&ctl.empty[s]), (g.debug == 8 || g.debug == 12) ? kAWarps : kBWarps);
+      pl::mbar_init(pl::smem_u32(&ctl.scanned[s]), kAPerGroup);
+      pl::mbar_init(pl::smem_u32(&ctl.empty[s]), (g.debug == 8 || g.debug == 12) ? kAPerGroup : kBWarps);
       ctl.wl_next[s] = 0u;
     }
     for (int q = 0; q < kNBuf; ++q) {
@@ -717,6 +720,10 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
         int qq = 0;                                     // chunk within the plane
         for (int q = 0; q < it.nchunks; ++q, ++gq) {
           const uint32_t s = gq & smask;
+          if ((gq & (kAGroups - 1)) != static_cast<uint32_t>((warp - kAWarp0) / kAPerGroup)) {   // the other group's chunk
+            if (++qq == it.cpp) qq = 0;
+            continue;
+          }
           {
             const long long w0 = RTM3D_CLK();
             pl::mbar_wait(pl::smem_u32(&ctl.full[s]), (gq >> sshift) & 1u, p.status, 0xE1000002u, 100);
@@ -727,24 +734,24 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
           const int c_lo = it.ys + qq * g.chunk_rows, c_hi = min(c_lo + g.chunk_rows, it.ye);
           if (++qq == it.cpp) qq = 0;
           const unsigned char* centre = ring + static_cast<size_t>(s) * g.stage_bytes + g.row_bytes;  // image row c_lo
-          const int aw = warp - kAWarp0;
+          const int aw = (warp - kAWarp0) % kAPerGroup;          // index within the group that scans this chunk
           // this A-warp's private segment of the stage's worklist: no atomics, the fill count lives in a register
           unsigned short* wl = wl_all + static_cast<size_t>(s) * g.wl_cap + static_cast<size_t>(aw) * g.wl_seg;
           int wn = 0;
           const int ng = (c_hi - c_lo) * gpr;
           const uint32_t lt = (1u << lane) - 1u;
-          // tasks of 32 groups: aw, aw + kAWarps, ...; kAUnroll of them per round, out-of-range groups read as -inf
+          // tasks of 32 groups: aw, aw + kAPerGroup, ...; kAUnroll of them per round, out-of-range groups read as -inf
           const unsigned char* lp = centre + (static_cast<size_t>(aw) * 32 + lane) * 16;
 #pragma unroll 1
-          for (int g0 = aw * 32 + lane; g0 - lane < ng; g0 += kAUnroll * kAWarps * 32, lp += kAUnroll * kAWarps * 512) {
+          for (int g0 = aw * 32 + lane; g0 - lane < ng; g0 += kAUnroll * kAPerGroup * 32, lp += kAUnroll * kAPerGroup * 512) {
             const float tf = fmaxf(L.t_filter, t_floor);
             float m[kAUnroll];
 #pragma unroll
             for (int u = 0; u < kAUnroll; ++u) {
               m[u] = -INFINITY;
-              if (g0 + u * kAWarps * 32 < ng) {
+              if (g0 + u * kAPerGroup * 32 < ng) {
                 float v[E];
-                Grp<T>::load(lp + u * kAWarps * 512, v);
+                Grp<T>::load(lp + u * kAPerGroup * 512, v);
                 m[u] = v[0];
 #pragma unroll
                 for (int i = 1; i < E; ++i) m[u] = fmaxf(m[u], v[i]);
@@ -752,13 +759,13 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
             }
             bool any = false;
 #pragma unroll
-            for (int u = 0; u < kAUnroll; ++u) any |= (m[u] >= tf) && (g0 + u * kAWarps * 32 < ng);
+            for (int u = 0; u < kAUnroll; ++u) any |= (m[u] >= tf) && (g0 + u * kAPerGroup * 32 < ng);
             if (!(g.debug == 4 || g.debug == 7 || g.debug == 12) && __any_sync(0xffffffffu, any)) {
 #pragma unroll
               for (int u = 0; u < kAUnroll; ++u) {
-                const bool hit = (m[u] >= tf) && (g0 + u * kAWarps * 32 < ng);
+                const bool hit = (m[u] >= tf) && (g0 + u * kAPerGroup * 32 < ng);
                 const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-                if (hit) wl[wn + __popc(bal & lt)] = static_cast<unsigned short>(g0 + u * kAWarps * 32);
+                if (hit) wl[wn + __popc(bal & lt)] = static_cast<unsigned short>(g0 + u * kAPerGroup * 32);
                 wn += __popc(bal);
               }
             }
@@ -807,10 +814,10 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
           const unsigned short* wl = wl_all + static_cast<size_t>(s) * g.wl_cap;
           const unsigned char* centre = ring + static_cast<size_t>(s) * g.stage_bytes + g.row_bytes;
           // the stage's worklist = the concatenation of the A-warps' segments
-          int seg_end[kAWarps];
+          int seg_end[kAPerGroup];
           int n = 0;
 #pragma unroll
-          for (int a = 0; a < kAWarps; ++a) { n += static_cast<int>(ctl.wl_count[s][a]); seg_end[a] = n; }
+          for (int a = 0; a < kAPerGroup; ++a) { n += static_cast<int>(ctl.wl_count[s][a]); seg_end[a] = n; }
           const int nb_batches = (g.debug == 1 || g.debug == 3 || g.debug == 7) ? 0 : ((n + 31) >> 5);
           if (warp == kBWarp0 && lane == 0) RTM3D_ACC(kStWlEntries, n);
           // Batches are handed out by a shared counter.  The stage is only needed for a batch's loads: the next batch is
@@ -834,7 +841,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
             if (wi < n) {
               int seg = 0, seg_begin = 0;
 #pragma unroll
-              for (int a = 0; a < kAWarps - 1; ++a) { if (wi >= seg_end[a]) { seg = a + 1; seg_begin = seg_end[a]; } }
+              for (int a = 0; a < kAPerGroup - 1; ++a) { if (wi >= seg_end[a]) { seg = a + 1; seg_begin = seg_end[a]; } }
               const int gi = wl[seg * g.wl_seg + (wi - seg_begin)];
               gp = centre + static_cast<size_t>(gi) * 16;
               Grp<T>::load(gp, v);
@@ -1234,7 +1241,7 @@ static bool make_plane_geom(const PlaneParams& p, int dtype, int split_override,
   int stages = kMaxStages;
   const size_t ring = budget - fixed;
   auto rows_for = [&](int st) {
-    const long long per_stage = static_cast<long long>(ring / st) - 2LL * row_bytes - 64 - 2LL * kAWarps * 64;
+    const long long per_stage = static_cast<long long>(ring / st) - 2LL * row_bytes - 64 - 2LL * kAPerGroup * 64;
     return static_cast<int>(per_stage * 8 / (9LL * row_bytes));       // cr*row_bytes + cr*row_bytes/8 <= per_stage
   };
   int cr = rows_for(stages);
@@ -1257,9 +1264,9 @@ static bool make_plane_geom(const PlaneParams& p, int dtype, int split_override,
   g.stage_bytes = (cr + 2) * row_bytes;
   {
     const int tasks = (cr * g.gpr + 31) / 32;                             // tasks of 32 groups in a chunk
-    const int per_warp = (tasks + kAWarps - 1) / kAWarps;                   // most tasks one A-warp gets
+    const int per_warp = (tasks + kAPerGroup - 1) / kAPerGroup;                   // most tasks one A-warp gets
     g.wl_seg = per_warp * 32;
-    g.wl_cap = kAWarps * g.wl_seg;
+    g.wl_cap = kAPerGroup * g.wl_seg;
   }
   g.n_items = static_cast<int>(static_cast<long long>(p.B) * ((p.C > 0 ? 1 : 0) + p.Cv) * split);
   g.smem = static_cast<unsigned>(static_cast<size_t>(stages) * (g.stage_bytes + 2ull * g.wl_cap) + fixed);
