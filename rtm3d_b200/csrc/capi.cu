@@ -300,8 +300,14 @@ int rtm3d_decode_fused(const void* hm, const void* off, const void* off2, const 
     if (int e = rtm3d_decode_main(hm, off, off2, dtype, B, C, H, W, n_vert, K, thresh, down, cls, score, proj, verts, bbox, flat,
                                   counts, ws, ws_bytes, flags, stream))
       return e;
+    // the two calls carve the workspace for different plane counts: what the first one left in the region the second
+    // one uses for its tickets must be cleared (each call leaves its OWN tickets clean)
+    const rtm3d::WorkspaceLayout Lk = rtm3d::workspace_layout(B, Cv, H, W, K);
+    if (int e = cuda_fail(static_cast<int>(cudaMemsetAsync(ws, 0, Lk.status_off, s)), "workspace ticket reset")) return e;
     if (int e = rtm3d_decode_keypoints(kpt_hm, voff2, dtype, B, Cv, H, W, K, kscore, kxy, kflat, ws, ws_bytes, flags, stream))
       return e;
+    const rtm3d::WorkspaceLayout Lm = rtm3d::workspace_layout(B, C, H, W, K);
+    if (int e = cuda_fail(static_cast<int>(cudaMemsetAsync(ws, 0, Lm.status_off, s)), "workspace ticket reset")) return e;
   }
   if (flags & RTM3D_FLAG_NO_GROUP) return 0;
   return rtm3d_group_vertices(flat, counts, off, off2, dtype, B, H, W, n_vert, K, kscore, kxy, Cv, down, kpt_proj, kpt_score,
