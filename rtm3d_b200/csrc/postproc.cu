@@ -109,6 +109,19 @@ int launch_epilogue_kpt(const EpiKptParams& p, int dtype, cudaStream_t s) {
 // search of _group_vertexs_kf, (3) per detection: 2D box, class, centre.  Arithmetic and association order are those of
 // epilogue_main_kernel, epilogue_kpt_kernel and group_vertices_kernel (bit-identical results).
 constexpr int kPostThreads = 512;
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  return static_cast<unsigned long long>(__float_as_uint(lo)) | (static_cast<unsigned long long>(__float_as_uint(hi)) << 32);
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 template <typename T>
 __global__ void __launch_bounds__(kPostThreads) post_fused_kernel(const PostFusedParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -173,12 +186,17 @@ __global__ void __launch_bounds__(kPostThreads) post_fused_kernel(const PostFuse
         if (p.verts_cv) { p.verts_cv[row * 2] = 0.f; p.verts_cv[row * 2 + 1] = 0.f; }
       } else {
         const float* cand = s_xy + static_cast<size_t>(k) * K * 2;
+        // (x, y) pairs go through the packed fp32x2 pipe (FADD2 / FMUL2: IEEE round-to-nearest per lane, the same
+        // results as the scalar ops, half the instructions)
+        const unsigned long long* cand2 = reinterpret_cast<const unsigned long long*>(cand);
+        const unsigned long long m2 = pack2(mx, my), o2 = pack2(ox, oy);
         float best = INFINITY;
         int bj = 0;
+#pragma unroll 4
         for (int j = 0; j < K; ++j) {
-          const float dx = __fsub_rn(__fsub_rn(cand[2 * j], mx), ox);
-          const float dy = __fsub_rn(__fsub_rn(cand[2 * j + 1], my), oy);
-          const float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+          const unsigned long long df = sub2(sub2(cand2[j], m2), o2);      // (v - m) - off      (models/model.py:147,149)
+          const unsigned long long sq = mul2(df, df);
+          const float d = __fadd_rn(__uint_as_float(static_cast<uint32_t>(sq)), __uint_as_float(static_cast<uint32_t>(sq >> 32)));
           if (d < best) { best = d; bj = j; }
         }
         p.kpt_proj[row * 2] = __fmul_rn(p.down, cand[2 * bj]);
