@@ -198,30 +198,70 @@ struct ItemInfo {
   uint32_t hw;                  // H*W: flat_base advances by it from plane to plane
 };
 
-// The items of a CTA: blockIdx.x, blockIdx.x + gridDim.x, ...  (item = (b * slots + slot) * split + strip; slot 0 = the image's main planes,
-// then one slot per keypoint plane), walked
-// without a division per item.
-struct ItemIter {
-  int item, b, r;               // r = item - b * per_img
-  int per_img, step, step_b, step_r;
-  __device__ __forceinline__ void init(int first, int step_, int per_img_) {
-    per_img = per_img_; step = step_;
-    item = first; b = first / per_img_; r = first - b * per_img_;
-    step_b = step_ / per_img_; step_r = step_ - step_b * per_img_;
+// Items are numbered heavy-first: the main items (one per image and strip: C planes in one flat top-K) and then the
+// keypoint items (one plane each), the strips of one problem next to each other:
+//   main item  i           = b * split + strip                      (i < n_main)
+//   keypoint   n_main + j,   j = (b * Cv + kc) * split + strip
+// A CTA takes main items blockIdx.x, blockIdx.x + gridDim.x, ... and then a contiguous run of keypoint items sized so
+// that every CTA streams about the same number of planes (a plain stride over image-major items gave some CTAs every
+// main item they could get and others none: 26 vs 17 planes per CTA at B=256, C=3, Cv=9 on 148 SMs).
+struct CtaItems {
+  int n_items, n_main, cta, grid;
+  int mains;            // main items of this CTA
+  int kpt_first;        // its first keypoint item (index j) ...
+  int count;            // ... and its total number of items
+  __device__ __forceinline__ void init(const PlaneParams& p, const PlaneGeom& g, int cta_, int grid_) {
+    n_items = g.n_items; cta = cta_; grid = grid_;
+    n_main = p.C > 0 ? p.B * g.split : 0;
+    const int n_kpt = n_items - n_main;
+    const int m_lo = n_main / grid, n_hi = n_main - m_lo * grid;
+    const long long units = static_cast<long long>(n_main) * p.C + n_kpt;
+    const int target = static_cast<int>((units + grid - 1) / grid);               // planes per CTA, rounded up
+    const int cap_hi = max(0, target - p.C * (m_lo + 1)), cap_lo = max(0, target - p.C * m_lo);
+    mains = m_lo + (cta < n_hi ? 1 : 0);
+    const long long first = cta < n_hi ? static_cast<long long>(cta) * cap_hi
+                                       : static_cast<long long>(n_hi) * cap_hi + static_cast<long long>(cta - n_hi) * cap_lo;
+    const long long left = static_cast<long long>(n_kpt) - first;
+    const int cap = cta < n_hi ? cap_hi : cap_lo;
+    kpt_first = static_cast<int>(first < n_kpt ? first : n_kpt);
+    count = mains + static_cast<int>(left < 0 ? 0 : (left < cap ? left : cap));
   }
-  __device__ __forceinline__ void next() {
-    item += step; b += step_b; r += step_r;
-    if (r >= per_img) { r -= per_img; ++b; }
+  // the CTA's kl-th item (n_items past the end)
+  __device__ __forceinline__ int at(int kl) const {
+    if (kl < mains) return cta + kl * grid;
+    return kl < count ? n_main + kpt_first + (kl - mains) : n_items;
   }
 };
 
+struct ItemIter {
+  const CtaItems* ci;
+  int kl, item;
+  __device__ __forceinline__ void init(const CtaItems* c) { ci = c; kl = 0; item = c->at(0); }
+  __device__ __forceinline__ void next() { ++kl; item = ci->at(kl); }
+};
+
+// index into the per-plane threshold memory of an item: 0 for a main item, C + kc for keypoint plane kc
+__device__ __forceinline__ int item_plane(const PlaneParams& p, const PlaneGeom& g, int n_main, int item) {
+  if (item < n_main) return 0;
+  return p.C + ((item - n_main) >> g.split_shift) % p.Cv;
+}
+
 __device__ __forceinline__ ItemInfo decode_item(const PlaneParams& p, const PlaneGeom& g, const ItemIter& ii, int elem_bytes) {
   ItemInfo it;
-  it.b = ii.b;
-  it.slot = ii.r >> g.split_shift;
-  it.strip = ii.r & (g.split - 1);
-  it.is_main = p.C > 0 && it.slot == 0;
-  it.kc = it.is_main ? -1 : it.slot - (p.C > 0 ? 1 : 0);
+  const int n_main = ii.ci->n_main;
+  it.is_main = ii.item < n_main;
+  if (it.is_main) {
+    it.b = ii.item >> g.split_shift;
+    it.strip = ii.item & (g.split - 1);
+    it.slot = 0;
+    it.kc = -1;
+  } else {
+    const int j = ii.item - n_main, u = j >> g.split_shift;
+    it.strip = j & (g.split - 1);
+    it.b = u / p.Cv;
+    it.kc = u - it.b * p.Cv;
+    it.slot = it.kc + (p.C > 0 ? 1 : 0);
+  }
   it.plane = it.is_main ? 0 : p.C + it.kc;
   it.nplanes = it.is_main ? p.C : 1;
   it.ys = (it.strip * p.H) >> g.split_shift;
@@ -610,9 +650,8 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
   __syncthreads();
 
   const int planes_per_img = p.C + p.Cv;
-  const int slots_per_img = (p.C > 0 ? 1 : 0) + p.Cv;
-  const int per_img = slots_per_img * g.split;
-  auto plane_of_slot = [&](int slot) { return (p.C > 0 && slot == 0) ? 0 : p.C + slot - (p.C > 0 ? 1 : 0); };
+  CtaItems cta_items;
+  cta_items.init(p, g, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x));
   // speculative start threshold for a plane index: a few bins below the boundary remembered for it, or for its segment
   auto spec_for_plane = [&](int pl) -> int {
     if (pl >= kMaxPlanes) return -1;
@@ -629,9 +668,9 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
   if (tid == 0 && g.speculate) {
     // the first items of this CTA start from what the previous launch remembered
     for (int q = 0; q < kNBuf; ++q) {
-      const long long item = static_cast<long long>(blockIdx.x) + static_cast<long long>(q) * gridDim.x;
+      const int item = cta_items.at(q);
       if (item < g.n_items) {
-        const int sb = spec_for_plane(plane_of_slot(static_cast<int>((item % per_img) >> g.split_shift)));
+        const int sb = spec_for_plane(item_plane(p, g, cta_items.n_main, item));
         ctl.sel[q].spec_bin = sb;
         ctl.sel[q].spec_t = filter_from_bin(sb);
       }
@@ -657,7 +696,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
       __syncthreads();               // every role is done with pass 0; the retry flags are visible
     }
     ItemIter ii;
-    ii.init(static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), per_img);
+    ii.init(&cta_items);
 
     if (warp == kProdWarp) {
       // ================================ producer ================================
@@ -1001,7 +1040,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
         // speculation skipped pixels only when its edge lies above the score floor; it was right iff at least K
         // candidates were found at or above that edge
         const bool spec_active = sb >= 1 && __uint_as_float(bin_edge_bits(sb)) > lim;
-        const bool failed = spec_active && bin < sb;
+        const bool failed = spec_active && bin < sb && g.debug == 0;   // (the timing experiments starve the histogram)
         const uint32_t cut = (bin >= 1) ? bin_edge_bits(bin) : 0u;
         const unsigned long long kstar = L.kstar;
         if (lane == 0 && it.plane < kMaxPlanes) ctl.guess_bin[it.plane] = failed ? -1 : bin;
@@ -1048,12 +1087,8 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
           L.reserve = 0; L.lock = 0; L.last_upd = 0; L.t_filter = -INFINITY; L.kstar = 0ull; L.last_bin = -1; L.b_done = 0;
           // speculative start threshold of the item that gets this buffer next (kNBuf items ahead, pass 0 only)
           int nsb = -1;
-          const long long nxt = static_cast<long long>(item) + static_cast<long long>(kNBuf) * ii.step;
-          if (g.speculate && pass == 0 && nxt < g.n_items) {
-            int rn = ii.r + kNBuf * ii.step_r;
-            while (rn >= per_img) rn -= per_img;
-            nsb = spec_for_plane(plane_of_slot(rn >> g.split_shift));
-          }
+          const int nxt = cta_items.at(ii.kl + kNBuf);           // (pass 0 walks every item: kl == ord)
+          if (g.speculate && pass == 0 && nxt < g.n_items) nsb = spec_for_plane(item_plane(p, g, cta_items.n_main, nxt));
           L.spec_bin = nsb;
           L.spec_t = filter_from_bin(nsb);          // (-inf for nsb < 1)
           __threadfence_block();
@@ -1101,7 +1136,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
           if (do_emit) {
             __threadfence();
             // units of this problem are contiguous items: the strips of the image's main item, or of one keypoint plane
-            const size_t unit0 = static_cast<size_t>(it.b) * per_img + static_cast<size_t>(it.slot) * g.split;
+            const size_t unit0 = static_cast<size_t>(item - it.strip);
             // gather the parts' sorted lists into finA at offsets u*K, then rank-merge into finB
             int total = 0;
 #pragma unroll 1
@@ -1173,9 +1208,10 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
   __syncthreads();
   if (blockIdx.x == 0 && tid < kMaxPlanes && ctl.guess_bin[tid] >= 0) p.guess[tid] = static_cast<uint32_t>(ctl.guess_bin[tid] + 1);
 #pragma unroll 1
-  for (int item = static_cast<int>(blockIdx.x) + tid * static_cast<int>(gridDim.x); item < g.n_items;
-       item += kPlaneThreads * static_cast<int>(gridDim.x))
+  for (int kl = tid; kl < cta_items.count; kl += kPlaneThreads) {
+    const int item = cta_items.at(kl);
     if (__ldcg(&p.retry[item]) != 0u) p.retry[item] = 0u;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
