@@ -2,6 +2,8 @@
 #include "common.cuh"
 #include "params.h"
 #include "postproc.h"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace rtm3d {
 
@@ -108,7 +110,7 @@ int launch_epilogue_kpt(const EpiKptParams& p, int dtype, cudaStream_t s) {
 // memory for the grouping), (2) per (detection n, channel k): the Tier A gathers / regress and the nearest-candidate
 // search of _group_vertexs_kf, (3) per detection: 2D box, class, centre.  Arithmetic and association order are those of
 // epilogue_main_kernel, epilogue_kpt_kernel and group_vertices_kernel (bit-identical results).
-constexpr int kPostThreads = 512;
+constexpr int kPostThreads = 256;
 __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
   return static_cast<unsigned long long>(__float_as_uint(lo)) | (static_cast<unsigned long long>(__float_as_uint(hi)) << 32);
 }
@@ -122,30 +124,44 @@ __device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigne
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+// A cluster of four CTAs per image, each with a quarter of the detections: small CTAs spread evenly over the SMs and a
+// CTA's (detection, channel) pairs fit one round of its threads.  Every CTA needs all of the image's candidates: each
+// computes a quarter and stores it into the shared memory of all four (distributed shared memory).
+constexpr int kPostSplit = 4;
 template <typename T>
-__global__ void __launch_bounds__(kPostThreads) post_fused_kernel(const PostFusedParams p) {
+__global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kPostThreads) post_fused_kernel(const PostFusedParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int b = blockIdx.x, tid = threadIdx.x;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int b = blockIdx.x / kPostSplit, half = static_cast<int>(cluster.block_rank()), tid = threadIdx.x;
   const int K = p.K, Cv = p.Cv, V = p.n_vert, HW = p.H * p.W;
-  float* s_xy = reinterpret_cast<float*>(smem_raw);                 // [Cv*K*2] candidate positions
-  float* s_v = s_xy + static_cast<size_t>(Cv) * K * 2;               // [K*V*2]  scaled regressed vertices (Tier A)
-  float* s_m = s_v + static_cast<size_t>(K) * V * 2;                 // [K*2]    unscaled centre (mx, my)
+  const int KP = K + 1;                                              // padded row: channels start in different banks
+  const int per = (K + kPostSplit - 1) / kPostSplit;                 // detections per CTA
+  const int n0 = half * per, n1 = min(K, n0 + per);
+  float* s_xy = reinterpret_cast<float*>(smem_raw);                 // [Cv][KP][2] candidate positions
+  float* s_v = s_xy + static_cast<size_t>(Cv) * KP * 2;              // [per*V*2]  scaled regressed vertices (Tier A)
+  float* s_m = s_v + static_cast<size_t>(per) * V * 2;               // [per*2]    unscaled centre (mx, my)
   const int n_det = p.counts[b];
   const T* voff2 = reinterpret_cast<const T*>(p.voff2) + static_cast<size_t>(b) * 2 * HW;
   const T* off2 = reinterpret_cast<const T*>(p.off2) + static_cast<size_t>(b) * 2 * HW;
   const T* off = reinterpret_cast<const T*>(p.off) + static_cast<size_t>(b) * 2 * V * HW;
   // ---- (1) candidates: index split + sub-pixel add (models/model.py:113-114, :55-57)
-  for (int i = tid; i < Cv * K; i += kPostThreads) {
+  const int cand_per = (Cv * K + kPostSplit - 1) / kPostSplit;
+  float2* peer_xy[kPostSplit];
+#pragma unroll
+  for (int r = 0; r < kPostSplit; ++r) peer_xy[r] = reinterpret_cast<float2*>(cluster.map_shared_rank(s_xy, r));
+  for (int i = half * cand_per + tid; i < min(Cv * K, (half + 1) * cand_per); i += kPostThreads) {
     const size_t row = static_cast<size_t>(b) * Cv * K + i;
     const int flat = p.kflat[row];
     const int yi = flat / p.W, xi = flat - yi * p.W;
     const float x = __fadd_rn(static_cast<float>(xi), sigmoid_ref(to_f32(voff2[flat])));
     const float y = __fadd_rn(static_cast<float>(yi), sigmoid_ref(to_f32(voff2[HW + flat])));
-    s_xy[2 * i] = x; s_xy[2 * i + 1] = y;
+    const int k = i / K, j = i - k * K;
+#pragma unroll
+    for (int r = 0; r < kPostSplit; ++r) peer_xy[r][k * KP + j] = make_float2(x, y);
     p.kxy[row * 2] = x; p.kxy[row * 2 + 1] = y;
   }
   // ---- centres of the detections (models/model.py:48-50)
-  for (int n = tid; n < K; n += kPostThreads) {
+  for (int n = n0 + tid; n < n1; n += kPostThreads) {
     float mx = 0.f, my = 0.f;
     if (n < n_det) {
       const int rem = p.flat[static_cast<size_t>(b) * K + n] % HW;
@@ -153,18 +169,18 @@ __global__ void __launch_bounds__(kPostThreads) post_fused_kernel(const PostFuse
       mx = __fadd_rn(static_cast<float>(xi), sigmoid_ref(to_f32(off2[rem])));
       my = __fadd_rn(static_cast<float>(yi), sigmoid_ref(to_f32(off2[HW + rem])));
     }
-    s_m[2 * n] = mx; s_m[2 * n + 1] = my;
+    s_m[2 * (n - n0)] = mx; s_m[2 * (n - n0) + 1] = my;
   }
-  __syncthreads();
+  cluster.sync();          // every CTA of the image has all candidates (and nobody writes into a peer after this)
   // ---- (2) per (detection, channel): vertex regress (models/model.py:63-69) + nearest candidate (:144-161)
   const int KC = (Cv > V ? Cv : V);                                   // channels that need work per detection
-  for (int w = tid; w < K * KC; w += kPostThreads) {
-    const int n = w / KC, k = w - n * KC;
+  for (int w = tid; w < (n1 - n0) * KC; w += kPostThreads) {
+    const int nl = w / KC, k = w - nl * KC, n = n0 + nl;
     const bool valid = n < n_det;
     float ox = 0.f, oy = 0.f, mx = 0.f, my = 0.f;
     if (valid) {
       const int rem = p.flat[static_cast<size_t>(b) * K + n] % HW;
-      mx = s_m[2 * n]; my = s_m[2 * n + 1];
+      mx = s_m[2 * nl]; my = s_m[2 * nl + 1];
       if (k < V) {
         ox = to_f32(off[static_cast<size_t>(2 * k) * HW + rem]);
         oy = to_f32(off[static_cast<size_t>(2 * k + 1) * HW + rem]);
@@ -173,7 +189,7 @@ __global__ void __launch_bounds__(kPostThreads) post_fused_kernel(const PostFuse
     const float vx = valid ? __fmul_rn(p.down, __fadd_rn(ox, mx)) : 0.f;
     const float vy = valid ? __fmul_rn(p.down, __fadd_rn(oy, my)) : 0.f;
     if (k < V) {
-      s_v[(n * V + k) * 2] = vx; s_v[(n * V + k) * 2 + 1] = vy;
+      s_v[(nl * V + k) * 2] = vx; s_v[(nl * V + k) * 2 + 1] = vy;
       float* vout = p.verts + ((static_cast<size_t>(b) * K + n) * V + k) * 2;
       vout[0] = vx; vout[1] = vy;
     }
@@ -185,20 +201,37 @@ __global__ void __launch_bounds__(kPostThreads) post_fused_kernel(const PostFuse
         p.kpt_j[row] = -1;
         if (p.verts_cv) { p.verts_cv[row * 2] = 0.f; p.verts_cv[row * 2 + 1] = 0.f; }
       } else {
-        const float* cand = s_xy + static_cast<size_t>(k) * K * 2;
+        const float* cand = s_xy + static_cast<size_t>(k) * KP * 2;
         // (x, y) pairs go through the packed fp32x2 pipe (FADD2 / FMUL2: IEEE round-to-nearest per lane, the same
-        // results as the scalar ops, half the instructions)
+        // results as the scalar ops, half the instructions).  Four independent (best, index) chains over j = 4i + u keep
+        // the compare/select dependency off the critical path; merged with torch.argmin's first-minimal-index rule.
         const unsigned long long* cand2 = reinterpret_cast<const unsigned long long*>(cand);
         const unsigned long long m2 = pack2(mx, my), o2 = pack2(ox, oy);
-        float best = INFINITY;
-        int bj = 0;
-#pragma unroll 4
-        for (int j = 0; j < K; ++j) {
+        auto dist = [&](int j) {
           const unsigned long long df = sub2(sub2(cand2[j], m2), o2);      // (v - m) - off      (models/model.py:147,149)
           const unsigned long long sq = mul2(df, df);
-          const float d = __fadd_rn(__uint_as_float(static_cast<uint32_t>(sq)), __uint_as_float(static_cast<uint32_t>(sq >> 32)));
-          if (d < best) { best = d; bj = j; }
+          return __fadd_rn(__uint_as_float(static_cast<uint32_t>(sq)), __uint_as_float(static_cast<uint32_t>(sq >> 32)));
+        };
+        float bd[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+        int bi[4] = {0, 0, 0, 0};
+        int j = 0;
+#pragma unroll 2
+        for (; j + 4 <= K; j += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float d = dist(j + u);
+            if (d < bd[u]) { bd[u] = d; bi[u] = j + u; }
+          }
         }
+        for (; j < K; ++j) {
+          const float d = dist(j);
+          if (d < bd[0]) { bd[0] = d; bi[0] = j; }      // (j is past every index chain 0 has seen)
+        }
+        float best = bd[0];
+        int bj = bi[0];
+#pragma unroll
+        for (int u = 1; u < 4; ++u)
+          if (bd[u] < best || (bd[u] == best && bi[u] < bj)) { best = bd[u]; bj = bi[u]; }
         p.kpt_proj[row * 2] = __fmul_rn(p.down, cand[2 * bj]);
         p.kpt_proj[row * 2 + 1] = __fmul_rn(p.down, cand[2 * bj + 1]);
         p.kpt_score[row] = p.kscore[(static_cast<size_t>(b) * Cv + k) * K + bj];
@@ -209,8 +242,9 @@ __global__ void __launch_bounds__(kPostThreads) post_fused_kernel(const PostFuse
   }
   __syncthreads();
   // ---- (3) per detection: class, centre, 2D box over the regressed vertices (models/model.py:70-73)
-  for (int n = tid; n < K; n += kPostThreads) {
+  for (int n = n0 + tid; n < n1; n += kPostThreads) {
     const size_t row = static_cast<size_t>(b) * K + n;
+    const int nl = n - n0;
     const bool valid = n < n_det;
     float lo_x = 0.f, lo_y = 0.f, hi_x = 0.f, hi_y = 0.f;
     int c = -1;
@@ -218,33 +252,35 @@ __global__ void __launch_bounds__(kPostThreads) post_fused_kernel(const PostFuse
       c = p.flat[row] / HW;
       lo_x = lo_y = INFINITY; hi_x = hi_y = -INFINITY;
       for (int v = 0; v < V; ++v) {
-        const float vx = s_v[(n * V + v) * 2], vy = s_v[(n * V + v) * 2 + 1];
+        const float vx = s_v[(nl * V + v) * 2], vy = s_v[(nl * V + v) * 2 + 1];
         lo_x = fminf(lo_x, vx); hi_x = fmaxf(hi_x, vx);
         lo_y = fminf(lo_y, vy); hi_y = fmaxf(hi_y, vy);
       }
     }
     p.cls[row] = c;
-    p.proj[row * 2] = valid ? __fmul_rn(p.down, s_m[2 * n]) : 0.f;
-    p.proj[row * 2 + 1] = valid ? __fmul_rn(p.down, s_m[2 * n + 1]) : 0.f;
+    p.proj[row * 2] = valid ? __fmul_rn(p.down, s_m[2 * nl]) : 0.f;
+    p.proj[row * 2 + 1] = valid ? __fmul_rn(p.down, s_m[2 * nl + 1]) : 0.f;
     p.bbox[row * 4 + 0] = lo_x; p.bbox[row * 4 + 1] = lo_y; p.bbox[row * 4 + 2] = hi_x; p.bbox[row * 4 + 3] = hi_y;
   }
 }
 
 size_t post_fused_smem(int Cv, int K, int n_vert) {
-  return (static_cast<size_t>(Cv) * K * 2 + static_cast<size_t>(K) * n_vert * 2 + static_cast<size_t>(K) * 2) * sizeof(float);
+  const size_t per = static_cast<size_t>((K + kPostSplit - 1) / kPostSplit);
+  return (static_cast<size_t>(Cv) * (K + 1) * 2 + per * n_vert * 2 + per * 2) * sizeof(float);
 }
 
 int launch_post_fused(const PostFusedParams& p, int dtype, cudaStream_t s) {
   const size_t smem = post_fused_smem(p.Cv, p.K, p.n_vert);
+  const unsigned grid = static_cast<unsigned>(p.B) * kPostSplit;
   cudaError_t e;
   if (dtype == 0) {
     e = cudaFuncSetAttribute(post_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
-    post_fused_kernel<float><<<p.B, kPostThreads, smem, s>>>(p);
+    post_fused_kernel<float><<<grid, kPostThreads, smem, s>>>(p);
   } else {
     e = cudaFuncSetAttribute(post_fused_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
-    post_fused_kernel<__nv_bfloat16><<<p.B, kPostThreads, smem, s>>>(p);
+    post_fused_kernel<__nv_bfloat16><<<grid, kPostThreads, smem, s>>>(p);
   }
   return static_cast<int>(cudaGetLastError());
 }
