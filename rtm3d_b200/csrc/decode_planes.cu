@@ -115,11 +115,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// The heat-maps are read once: their lines are the first to leave L2 (`policy` = evict_first), so that the sectors the
-// finishers prefetch for the post kernel (below) are still there when it runs.
+// The heat-maps are read once: their lines are the first to leave L2 (`policy` = evict_first), which keeps the
+// selection outputs the post kernel reads next (score / flat / kflat) resident.
 __device__ __forceinline__ unsigned long long l2_policy_evict_first() {
   unsigned long long pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_normal() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, unsigned long long policy) {
@@ -127,9 +132,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar), "l"(policy)
                : "memory");
 }
-// Fire-and-forget: bring the 32-byte sector of a regression-map scalar into L2 (the post kernel gathers it a few
-// microseconds later; issued here the DRAM access overlaps the streaming instead of serialising behind it).
-__device__ __forceinline__ void prefetch_l2(const void* a) { asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(a)); }
 __device__ __forceinline__ void fence_sc_cta() { asm volatile("fence.sc.cta;" ::: "memory"); }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -562,10 +564,8 @@ __device__ __forceinline__ void warp_fin_sort(unsigned long long* a, int m, unsi
 // Tier A selection of image b: score, flat index (and the count) of the `cnt` sorted keys; rows >= cnt get score 0 and
 // flat -1.  The gathers / regress / 2D box of models/model.py:47-50,63-73 run afterwards in epilogue_main_kernel, wide
 // over the batch, so that their scattered reads do not stall a streaming CTA.
-static __device__ __noinline__ void warp_write_main(const PlaneParams& p, int b, const unsigned long long* sorted, int cnt, int lane,
-                                                    int es) {
+static __device__ __noinline__ void warp_write_main(const PlaneParams& p, int b, const unsigned long long* sorted, int cnt, int lane) {
   const int K = p.K;
-  const size_t HW = static_cast<size_t>(p.H) * p.W;
 #pragma unroll 1
   for (int j = lane; j < K; j += 32) {
     const size_t row = static_cast<size_t>(b) * K + j;
@@ -573,15 +573,6 @@ static __device__ __noinline__ void warp_write_main(const PlaneParams& p, int b,
     const unsigned long long key = valid ? sorted[j] : 0ull;
     p.score[row] = valid ? key_score(key) : 0.f;
     p.flat[row] = valid ? static_cast<int32_t>(key_flat(key)) : -1;
-    if (valid && p.off && p.off2_main) {
-      const size_t rem = key_flat(key) % static_cast<uint32_t>(HW);
-      const unsigned char* o = reinterpret_cast<const unsigned char*>(p.off) + (static_cast<size_t>(b) * 2 * p.n_vert * HW + rem) * es;
-#pragma unroll 1
-      for (int ch = 0; ch < 2 * p.n_vert; ++ch) pl::prefetch_l2(o + static_cast<size_t>(ch) * HW * es);
-      const unsigned char* o2 = reinterpret_cast<const unsigned char*>(p.off2_main) + (static_cast<size_t>(b) * 2 * HW + rem) * es;
-      pl::prefetch_l2(o2);
-      pl::prefetch_l2(o2 + HW * es);
-    }
   }
   if (lane == 0) p.counts[b] = cnt;
 }
@@ -591,7 +582,7 @@ static __device__ __noinline__ void warp_write_main(const PlaneParams& p, int b,
 // App. A).  The sub-pixel add (models/model.py:113-114, :55-57) runs afterwards in epilogue_kpt_kernel.
 //   scratch: >= 3K+8 words of shared memory of this warp.
 static __device__ __noinline__ void warp_write_kpt(const PlaneParams& p, int b, int c, const unsigned long long* sorted, int cnt,
-                                                   uint32_t* scratch, int lane, int es) {
+                                                   uint32_t* scratch, int lane) {
   const int K = p.K, HW = p.H * p.W;
   uint32_t* fill = scratch + 2 * K;             // [K] filler indices (rows cnt..K-1)
   if (cnt < K) {
@@ -616,15 +607,8 @@ static __device__ __noinline__ void warp_write_kpt(const PlaneParams& p, int b, 
 #pragma unroll 1
   for (int j = lane; j < K; j += 32) {
     const size_t row = (static_cast<size_t>(b) * p.Cv + c) * K + j;
-    const uint32_t fl = j < cnt ? key_flat(sorted[j]) : fill[j];
     p.kscore[row] = j < cnt ? key_score(sorted[j]) : 0.0f;
-    p.kflat[row] = static_cast<int32_t>(fl);
-    if (p.off2_kpt) {
-      const unsigned char* o2 = reinterpret_cast<const unsigned char*>(p.off2_kpt) +
-                                (static_cast<size_t>(b) * 2 * p.H * p.W + fl) * es;
-      pl::prefetch_l2(o2);
-      pl::prefetch_l2(o2 + static_cast<size_t>(p.H) * p.W * es);
-    }
+    p.kflat[row] = static_cast<int32_t>(j < cnt ? key_flat(sorted[j]) : fill[j]);
   }
   __syncwarp();
 }
@@ -729,7 +713,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
     if (warp == kProdWarp) {
       // ================================ producer ================================
       if (lane == 0) {
-        const unsigned long long stream_policy = pl::l2_policy_evict_first();
+        const unsigned long long stream_policy = g.debug == 13 ? pl::l2_policy_evict_normal() : pl::l2_policy_evict_first();
         for (; ii.item < g.n_items; ii.next()) {
           if (pass == 1 && __ldcg(&p.retry[ii.item]) == 0u) continue;
           const ItemInfo it = decode_item(p, g, ii, static_cast<int>(sizeof(T)));
@@ -1219,8 +1203,8 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
         RTM3D_FIN_LAP(kStFinPublish);
         if (g.debug == 6 || (g.debug == 9 && it.is_main) || (g.debug == 10 && !it.is_main)) continue;
         if (do_emit) {
-          if (it.is_main) warp_write_main(sp, it.b, finB, have, lane, static_cast<int>(sizeof(T)));
-          else warp_write_kpt(sp, it.b, kc, finB, have, fin_scratch, lane, static_cast<int>(sizeof(T)));
+          if (it.is_main) warp_write_main(sp, it.b, finB, have, lane);
+          else warp_write_kpt(sp, it.b, kc, finB, have, fin_scratch, lane);
         }
         __syncwarp();
         RTM3D_FIN_LAP(kStFinEmit);
