@@ -997,16 +997,9 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
           __syncwarp();
           if (!released && lane == 0) pl::mbar_arrive(pl::smem_u32(&ctl.empty[s]));
           if (q == it.nchunks - 1) {
-            // the last B-warp to leave the item brings the histogram boundary up to date for the finisher
-            int last = 0;
-            if (lane == 0) { __threadfence_block(); last = (atomicAdd(&L.b_done, 1u) == static_cast<uint32_t>(kBWarps - 1)); }
-            last = __shfl_sync(0xffffffffu, last, 0);
-            if (last) {
-              __threadfence_block();
-              update_threshold(L, hist, K, lane);
-              __syncwarp();
-            }
-            if (lane == 0) pl::mbar_arrive(pl::smem_u32(&ctl.item_done[buf]));
+            // (the finisher derives the final histogram boundary itself: a B-warp that did it here would be late for the
+            // next chunks, and every stage waits for every B-warp)
+            if (lane == 0) { __threadfence_block(); pl::mbar_arrive(pl::smem_u32(&ctl.item_done[buf])); }
           }
           if (lane == 0) RTM3D_ACC(kStBBusy, RTM3D_CLK() - bb0);
         }
@@ -1047,8 +1040,8 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
         const int n = min(static_cast<int>(L.reserve), g.list_cap);
         const float lim = it.is_main ? p.thresh : 0.0f;
 
-        // ---- final boundary (kept up to date by the last B-warp); was the speculative start threshold justified?
-        const int bin = L.last_bin;
+        // ---- final boundary of the histogram; was the speculative start threshold justified?
+        const int bin = warp_hist_boundary(hist, K, lane);
         const int sb = L.spec_bin;
         // speculation skipped pixels only when its edge lies above the score floor; it was right iff at least K
         // candidates were found at or above that edge
