@@ -123,6 +123,7 @@ const char* rtm3d_build_info(void) {
 
 /* developer instrumentation (tools/plane_stats.py); deliberately absent from include/rtm3d_decode.h */
 void rtm3d_debug_set_copy_rows(int rows) { rtm3d::debug_set_copy_rows(rows); }
+void rtm3d_debug_set_trace(void* t) { rtm3d::debug_set_trace(static_cast<unsigned long long*>(t)); }
 void rtm3d_debug_set_stats(void* dev_u64_16) { rtm3d::debug_set_stats(static_cast<unsigned long long*>(dev_u64_16)); }
 
 int rtm3d_decode_workspace_bytes(int B, int C, int H, int W, int K, size_t* out_bytes) {

@@ -162,6 +162,13 @@ enum StatSlot { kStItems = 0, kStRetried, kStWlEntries, kStBatches, kStPushed, k
 #define RTM3D_ACC(slot, val) do { if constexpr (STATS) acc_[slot] += static_cast<long long>(val); } while (0)
 #define RTM3D_CLK() (STATS ? clock64() : 0ll)
 #define RTM3D_FLUSH(slot) do { if constexpr (STATS) { if (p.stats && acc_[slot] != 0) { atomicAdd(&p.stats[slot], static_cast<unsigned long long>(acc_[slot])); acc_[slot] = 0; } } } while (0)
+// Per-chunk timestamps of CTA 0 (tools/trace_cta.py): compiled in only with -DRTM3D_CHUNK_TRACE -- even a predicated-off
+// mark in the per-chunk loops of every role costs ~10% of the kernel.
+#ifdef RTM3D_CHUNK_TRACE
+#define RTM3D_MARK(kind, idx) do { if (!STATS && p.stats && blockIdx.x == 0 && (idx) < 96u) p.stats[(kind) * 96 + (idx)] = static_cast<unsigned long long>(clock64()); } while (0)
+#else
+#define RTM3D_MARK(kind, idx) do { } while (0)
+#endif
 #define RTM3D_TRACE(ev) do { if constexpr (STATS) { if (p.stats && blockIdx.x == 0 && lane == 0 && trace_n < 960) { p.stats[64 + trace_n] = (static_cast<unsigned long long>(ev) << 56) | (static_cast<unsigned long long>(clock64()) & 0x00FFFFFFFFFFFFFFull); ++trace_n; } } } while (0)
 #define RTM3D_FIN_LAP(slot) do { if constexpr (STATS) { if (lane == 0) { const long long now_ = clock64(); acc_[slot] += now_ - lap_; lap_ = now_; } } } while (0)
 
@@ -192,6 +199,7 @@ struct __align__(16) PlaneCtl {
   uint32_t rsel[kNBuf + kFinWarps][264];   // radix-select scratch: [buf] B-warp compaction of that buffer, [kNBuf + w] finisher warp w
   uint32_t fin_next;            // next item ordinal to hand to a finisher warp
   volatile uint32_t fin_released[kNBuf];   // how many times the finishers have handed selection buffer [buf] back
+  uint32_t n_retry;             // items of this CTA whose speculative start threshold failed (redone in pass 1)
   volatile int guess_bin[kMaxPlanes];       // final boundary bin of the last finished item of each plane index (-1 = unknown)
 };
 
@@ -621,6 +629,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
 
   constexpr int E = Grp<T>::E;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (!STATS && p.stats && tid == 0) p.stats[3840 + 4 * blockIdx.x + 0] = pl::globaltimer_ns();
   const int W = p.W, H = p.H, K = p.K;
   const int S = g.stages;                        // power of two
   const uint32_t smask = static_cast<uint32_t>(S - 1);
@@ -651,10 +660,10 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
       ctl.fin_released[q] = 0u;
     }
     ctl.fin_next = 0u;
-#pragma unroll 1
-    for (int q = 0; q < kMaxPlanes; ++q) ctl.guess_bin[q] = static_cast<int>(__ldcg(&p.guess[q])) - 1;   // remembered from the previous launch
+    ctl.n_retry = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (tid >= 64 && tid < 64 + kMaxPlanes) ctl.guess_bin[tid - 64] = static_cast<int>(__ldcg(&p.guess[tid - 64])) - 1;   // remembered from the previous launch
 #pragma unroll 1
   for (int i = tid; i < kNBuf * kHistBins; i += kPlaneThreads) hist_all[i] = 0u;
 #pragma unroll 1
@@ -702,10 +711,13 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
   int trace_n = 0;
   (void)trace_n;
 
+  if (!STATS && p.stats && tid == 0) p.stats[3840 + 4 * blockIdx.x + 1] = pl::globaltimer_ns();
   for (int pass = 0; pass < 2; ++pass) {
     if (pass == 1) {
       __threadfence();
       __syncthreads();               // every role is done with pass 0; the retry flags are visible
+      if (!STATS && p.stats && tid == 0) p.stats[3840 + 4 * blockIdx.x + 2] = pl::globaltimer_ns();
+      if (ctl.n_retry == 0u) break;  // (nearly always)
     }
     ItemIter ii;
     ii.init(&cta_items);
@@ -742,6 +754,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
               const uint32_t piece = static_cast<uint32_t>(g.copy_rows) * g.row_bytes;
               for (uint32_t o2 = 0; o2 < bytes; o2 += piece)
                 pl::bulk_g2s(dst + o2, src + o2, min(piece, bytes - o2), bar, stream_policy);
+              RTM3D_MARK(0, gq);
             }
             if (++qq == it.cpp) { qq = 0; ++pli; }
           }
@@ -779,6 +792,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
           {
             const long long w0 = RTM3D_CLK();
             pl::mbar_wait(pl::smem_u32(&ctl.full[s]), (gq >> sshift) & 1u, p.status, 0xE1000002u, 100);
+            if (lane == 0) RTM3D_MARK(1 + (warp - kAWarp0) % kAPerGroup, gq);
             if (lane == 0) RTM3D_ACC(kStWaitFull, RTM3D_CLK() - w0);
           }
           const long long al0 = RTM3D_CLK();
@@ -826,6 +840,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
           if (warp == kAWarp0) RTM3D_TRACE(2);
           __syncwarp();
           if (lane == 0) pl::mbar_arrive(pl::smem_u32((g.debug == 8 || g.debug == 12) ? &ctl.empty[s] : &ctl.scanned[s]));
+          if (lane == 0) RTM3D_MARK(5 + (warp - kAWarp0) % kAPerGroup, gq);
           if (warp == kAWarp0) RTM3D_TRACE(4);
           if (lane == 0) RTM3D_ACC(kStALoop, RTM3D_CLK() - al0);
         }
@@ -857,6 +872,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
           {
             const long long w0 = RTM3D_CLK();
             pl::mbar_wait(pl::smem_u32(&ctl.scanned[s]), (gq >> sshift) & 1u, p.status, 0xE1000005u, 100);
+            if (lane == 0) RTM3D_MARK(10 + (warp - kBWarp0), gq);
             if (lane == 0) RTM3D_ACC(kStWaitScanned, RTM3D_CLK() - w0);
           }
           const long long bb0 = RTM3D_CLK();
@@ -931,6 +947,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
             if (bt >= nb_batches && !released) {
               __syncwarp();
               if (lane == 0) pl::mbar_arrive(pl::smem_u32(&ctl.empty[s]));
+              if (lane == 0) RTM3D_MARK(17 + (warp - kBWarp0), gq);
               released = true;
             }
             // per-lane candidate loop; a lane that finds the list full parks (`stuck`) until the warp has made room
@@ -996,6 +1013,8 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
           }
           __syncwarp();
           if (!released && lane == 0) pl::mbar_arrive(pl::smem_u32(&ctl.empty[s]));
+          if (!released && lane == 0) RTM3D_MARK(17 + (warp - kBWarp0), gq);
+          if (lane == 0) RTM3D_MARK(24 + (warp - kBWarp0), gq);
           if (q == it.nchunks - 1) {
             // (the finisher derives the final histogram boundary itself: a B-warp that did it here would be late for the
             // next chunks, and every stage waits for every B-warp)
@@ -1106,7 +1125,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
         RTM3D_FIN_LAP(kStFinRelease);
         if (g.debug == 2 || g.debug == 3 || g.debug == 7) continue;
         if (failed) {
-          if (lane == 0) { p.retry[item] = 1u; RTM3D_ACC(kStRetried, 1); }   // redone in pass 1 (no speculation there)
+          if (lane == 0) { p.retry[item] = 1u; atomicAdd(&ctl.n_retry, 1u); RTM3D_ACC(kStRetried, 1); }   // redone in pass 1 (no speculation there)
           continue;
         }
         // ---- sort the survivors
@@ -1212,17 +1231,22 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
   }
   // leave the workspace clean: clear this CTA's retry flags once every role has finished reading them
   __syncthreads();
+  if (!STATS && p.stats && tid == 0) p.stats[3840 + 4 * blockIdx.x + 3] = pl::globaltimer_ns();
   if (blockIdx.x == 0 && tid < kMaxPlanes && ctl.guess_bin[tid] >= 0) p.guess[tid] = static_cast<uint32_t>(ctl.guess_bin[tid] + 1);
 #pragma unroll 1
-  for (int kl = tid; kl < cta_items.count; kl += kPlaneThreads) {
-    const int item = cta_items.at(kl);
-    if (__ldcg(&p.retry[item]) != 0u) p.retry[item] = 0u;
+  if (ctl.n_retry != 0u) {
+    for (int kl = tid; kl < cta_items.count; kl += kPlaneThreads) {
+      const int item = cta_items.at(kl);
+      if (__ldcg(&p.retry[item]) != 0u) p.retry[item] = 0u;
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 static int g_sm_count = 0;
 static unsigned long long* g_stats = nullptr;
+static unsigned long long* g_trace = nullptr;
+void debug_set_trace(unsigned long long* t) { g_trace = t; }
 static int g_copy_rows = 0;   // developer knob (debug_set_copy_rows): rows per bulk copy, 0 = whole chunk
 void debug_set_copy_rows(int r) { g_copy_rows = r; }
 void debug_set_stats(unsigned long long* dev_u64_16) { g_stats = dev_u64_16; }
@@ -1337,7 +1361,7 @@ int launch_planes(const PlaneParams& p, int dtype, int split_override, int specu
   g.max_ctas = max_ctas;
   g.debug = debug;
   PlaneParams q = p;
-  q.stats = g_stats;
+  q.stats = g_stats ? g_stats : g_trace;
   if (g_stats) return dtype == 0 ? launch_planes_t<float, true>(q, g, s) : launch_planes_t<__nv_bfloat16, true>(q, g, s);
   return dtype == 0 ? launch_planes_t<float, false>(q, g, s) : launch_planes_t<__nv_bfloat16, false>(q, g, s);
 }

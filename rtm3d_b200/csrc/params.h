@@ -71,6 +71,7 @@ bool planes_eligible(const PlaneParams& p, int dtype);
 constexpr int kPlanesMaxSplit = 8;
 int threshold_table_bins();
 void debug_set_stats(unsigned long long* dev_u64_16);
+void debug_set_trace(unsigned long long* dev_u64_960);
 void debug_set_copy_rows(int rows);   // developer instrumentation, not part of the public ABI
 int launch_threshold_table(float* t, uint32_t* edge, cudaStream_t s);
 
