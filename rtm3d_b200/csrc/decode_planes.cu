@@ -43,8 +43,8 @@
 namespace rtm3d {
 
 constexpr int kAWarps = 8;               // threshold-filter warps (phase A), two per SM sub-partition
-constexpr int kAGroups = 2;              // A-warp groups: group g scans the chunks with (chunk number % kAGroups) == g, so that
-                                         // kAGroups chunks are being filtered at any time
+constexpr int kAGroups = 1;              // A-warp groups: group g scans the chunks with (chunk number % kAGroups) == g, so that
+                                         // kAGroups chunks are being filtered at any time (one group of all eight: half the scan latency per chunk)
 constexpr int kAPerGroup = kAWarps / kAGroups;
 constexpr int kBWarps = 7;               // peak-test / candidate warps (phase B)
 constexpr int kFinWarps = 4;              // each finishes whole items on its own (ticket order)
@@ -621,8 +621,11 @@ static __device__ __noinline__ void warp_write_kpt(const PlaneParams& p, int b, 
   __syncwarp();
 }
 
-template <typename T, bool STATS>
+// DBG: the timing experiments of PlaneGeom::debug are compiled in (tools/debug_time.py); the production instantiation
+// carries none of their tests -- every instruction on a role's per-chunk path counts.
+template <typename T, bool STATS, bool DBG>
 __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const PlaneParams p, const PlaneGeom g) {
+  const int dbg = DBG ? g.debug : 0;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ PlaneCtl ctl;
   __shared__ PlaneParams sp;     // copy for the out-of-line finisher code (keeps the kernel parameters out of local memory)
@@ -648,7 +651,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
     for (int s = 0; s < S; ++s) {
       pl::mbar_init(pl::smem_u32(&ctl.full[s]), 1);
       pl::mbar_init(pl::smem_u32(&ctl.scanned[s]), kAPerGroup);
-      pl::mbar_init(pl::smem_u32(&ctl.empty[s]), (g.debug == 8 || g.debug == 12) ? kAPerGroup : kBWarps);
+      pl::mbar_init(pl::smem_u32(&ctl.empty[s]), (dbg == 8 || dbg == 12) ? kAPerGroup : kBWarps);
       ctl.wl_next[s] = 0u;
     }
     for (int q = 0; q < kNBuf; ++q) {
@@ -725,7 +728,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
     if (warp == kProdWarp) {
       // ================================ producer ================================
       if (lane == 0) {
-        const unsigned long long stream_policy = g.debug == 13 ? pl::l2_policy_evict_normal() : pl::l2_policy_evict_first();
+        const unsigned long long stream_policy = dbg == 13 ? pl::l2_policy_evict_normal() : pl::l2_policy_evict_first();
         for (; ii.item < g.n_items; ii.next()) {
           if (pass == 1 && __ldcg(&p.retry[ii.item]) == 0u) continue;
           const ItemInfo it = decode_item(p, g, ii, static_cast<int>(sizeof(T)));
@@ -769,7 +772,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
         if (pass == 1 && __ldcg(&p.retry[ii.item]) == 0u) continue;
         const ItemInfo it = decode_item(p, g, ii, static_cast<int>(sizeof(T)));
         const int buf = static_cast<int>(k & (kNBuf - 1));
-        if (k >= static_cast<uint32_t>(kNBuf) && !(g.debug == 8 || g.debug == 12)) {
+        if (k >= static_cast<uint32_t>(kNBuf) && !(dbg == 8 || dbg == 12)) {
           const long long w0 = RTM3D_CLK();
           pl::mbar_wait(pl::smem_u32(&ctl.buf_free[buf]), ((k >> kBufShift) - 1u) & 1u, p.status, 0xE1000003u, 64);
           if (lane == 0) RTM3D_ACC(kStWaitBufFree, RTM3D_CLK() - w0);
@@ -826,7 +829,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
             bool any = false;
 #pragma unroll
             for (int u = 0; u < kAUnroll; ++u) any |= (m[u] >= tf) && (g0 + u * kAPerGroup * 32 < ng);
-            if (!(g.debug == 4 || g.debug == 7 || g.debug == 12) && __any_sync(0xffffffffu, any)) {
+            if (!(dbg == 4 || dbg == 7 || dbg == 12) && __any_sync(0xffffffffu, any)) {
 #pragma unroll
               for (int u = 0; u < kAUnroll; ++u) {
                 const bool hit = (m[u] >= tf) && (g0 + u * kAPerGroup * 32 < ng);
@@ -839,7 +842,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
           if (lane == 0) ctl.wl_count[s][aw] = static_cast<uint32_t>(wn);
           if (warp == kAWarp0) RTM3D_TRACE(2);
           __syncwarp();
-          if (lane == 0) pl::mbar_arrive(pl::smem_u32((g.debug == 8 || g.debug == 12) ? &ctl.empty[s] : &ctl.scanned[s]));
+          if (lane == 0) pl::mbar_arrive(pl::smem_u32((dbg == 8 || dbg == 12) ? &ctl.empty[s] : &ctl.scanned[s]));
           if (lane == 0) RTM3D_MARK(5 + (warp - kAWarp0) % kAPerGroup, gq);
           if (warp == kAWarp0) RTM3D_TRACE(4);
           if (lane == 0) RTM3D_ACC(kStALoop, RTM3D_CLK() - al0);
@@ -847,7 +850,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
       }
       if (lane == 0) RTM3D_ACC(kStATotal, RTM3D_CLK() - a_t0);
       RTM3D_FLUSH(kStATotal); RTM3D_FLUSH(kStWaitBufFree); RTM3D_FLUSH(kStWaitFull); RTM3D_FLUSH(kStALoop); RTM3D_FLUSH(kStASetup);
-    } else if (g.debug == 8 || g.debug == 12) {
+    } else if (dbg == 8 || dbg == 12) {
       // (timing experiment: producer + A-warps only)
     } else if (warp >= kBWarp0) {
       // ================================ B-warps: peak test, candidates ================================
@@ -886,7 +889,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
           int n = 0;
 #pragma unroll
           for (int a = 0; a < kAPerGroup; ++a) { n += static_cast<int>(ctl.wl_count[s][a]); seg_end[a] = n; }
-          const int nb_batches = (g.debug == 1 || g.debug == 3 || g.debug == 7) ? 0 : ((n + 31) >> 5);
+          const int nb_batches = (dbg == 1 || dbg == 3 || dbg == 7) ? 0 : ((n + 31) >> 5);
           if (warp == kBWarp0 && lane == 0) RTM3D_ACC(kStWlEntries, n);
           // Batches are handed out by a shared counter.  The stage is only needed for a batch's loads: the next batch is
           // claimed right after them, and when there is none the stage goes back to the producer BEFORE this warp works
@@ -1065,7 +1068,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
         // speculation skipped pixels only when its edge lies above the score floor; it was right iff at least K
         // candidates were found at or above that edge
         const bool spec_active = sb >= 1 && __uint_as_float(bin_edge_bits(sb)) > lim;
-        const bool failed = spec_active && bin < sb && g.debug == 0;   // (the timing experiments starve the histogram)
+        const bool failed = spec_active && bin < sb && dbg == 0;   // (the timing experiments starve the histogram)
         const uint32_t cut = (bin >= 1) ? bin_edge_bits(bin) : 0u;
         const unsigned long long kstar = L.kstar;
         if (lane == 0 && it.plane < kMaxPlanes) ctl.guess_bin[it.plane] = failed ? -1 : bin;
@@ -1123,7 +1126,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
         }
         my_ticket = __shfl_sync(0xffffffffu, my_ticket, 0);
         RTM3D_FIN_LAP(kStFinRelease);
-        if (g.debug == 2 || g.debug == 3 || g.debug == 7) continue;
+        if (dbg == 2 || dbg == 3 || dbg == 7) continue;
         if (failed) {
           if (lane == 0) { p.retry[item] = 1u; atomicAdd(&ctl.n_retry, 1u); RTM3D_ACC(kStRetried, 1); }   // redone in pass 1 (no speculation there)
           continue;
@@ -1136,7 +1139,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
         warp_fin_sort(finA, m, finB, lane);
         int have = min(m, K);
         RTM3D_FIN_LAP(kStFinSort);
-        if (g.debug == 5) continue;
+        if (dbg == 5) continue;
 
         // ---- emit, or publish + merge by the last part of the problem
         const int parts = g.split;                     // strips of the problem (image, or keypoint plane)
@@ -1213,7 +1216,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
           }
         }
         RTM3D_FIN_LAP(kStFinPublish);
-        if (g.debug == 6 || (g.debug == 9 && it.is_main) || (g.debug == 10 && !it.is_main)) continue;
+        if (dbg == 6 || (dbg == 9 && it.is_main) || (dbg == 10 && !it.is_main)) continue;
         if (do_emit) {
           if (it.is_main) warp_write_main(sp, it.b, finB, have, lane);
           else warp_write_kpt(sp, it.b, kc, finB, have, fin_scratch, lane);
@@ -1344,9 +1347,9 @@ bool planes_eligible(const PlaneParams& p, int dtype) {
   return make_plane_geom(p, dtype, 0, 1, g);
 }
 
-template <typename T, bool STATS>
+template <typename T, bool STATS, bool DBG>
 static int launch_planes_t(const PlaneParams& p, const PlaneGeom& g, cudaStream_t s) {
-  auto kern = decode_planes_kernel<T, STATS>;
+  auto kern = decode_planes_kernel<T, STATS, DBG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   int grid = g.n_items < g_sm_count ? g.n_items : g_sm_count;
@@ -1362,8 +1365,9 @@ int launch_planes(const PlaneParams& p, int dtype, int split_override, int specu
   g.debug = debug;
   PlaneParams q = p;
   q.stats = g_stats ? g_stats : g_trace;
-  if (g_stats) return dtype == 0 ? launch_planes_t<float, true>(q, g, s) : launch_planes_t<__nv_bfloat16, true>(q, g, s);
-  return dtype == 0 ? launch_planes_t<float, false>(q, g, s) : launch_planes_t<__nv_bfloat16, false>(q, g, s);
+  if (g_stats) return dtype == 0 ? launch_planes_t<float, true, false>(q, g, s) : launch_planes_t<__nv_bfloat16, true, false>(q, g, s);
+  if (debug != 0) return dtype == 0 ? launch_planes_t<float, false, true>(q, g, s) : launch_planes_t<__nv_bfloat16, false, true>(q, g, s);
+  return dtype == 0 ? launch_planes_t<float, false, false>(q, g, s) : launch_planes_t<__nv_bfloat16, false, false>(q, g, s);
 }
 
 // Verification aid: the logit threshold and the score edge of every histogram bin (rtm3d_threshold_table).
