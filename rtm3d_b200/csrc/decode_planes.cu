@@ -62,13 +62,14 @@ constexpr int kHistBins = 1664;          // score histogram: 64 bins per octave 
 constexpr int kScoreShift = 17;
 constexpr uint32_t kScoreBase = 0x33800000u >> kScoreShift; // bits of 2^-24
 constexpr int kMaxStages = 4;
+constexpr int kDefaultStages = 2;        // few, large stages: a chunk costs every role a fixed ~1 us of hand-offs whatever its size
+                                         // (measured: 2 x 64 KB beats 3 x 43 KB and 4 x 33 KB by 2-4 % on cfg2/4/5)
 constexpr int kMaxPlanes = 64;           // plane indices with a remembered threshold (speculation)
 constexpr int kSpecMargin = 1;           // bins below the remembered boundary the speculative threshold starts at
 constexpr int kUpdateEvery = 48;         // appended keys between two threshold updates
 
 struct PlaneGeom {
   int stages;         // ring depth (power of two)
-  int stage_shift;    // log2(stages)
   int speculate;      // 1: start items at the threshold remembered from the previous item of the same plane index
   int chunk_rows;     // centre rows per chunk
   int copy_rows;      // rows per bulk copy (a chunk = ceil((chunk_rows + 2) / copy_rows) copies on one barrier)
@@ -635,8 +636,6 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
   if (!STATS && p.stats && tid == 0) p.stats[3840 + 4 * blockIdx.x + 0] = pl::globaltimer_ns();
   const int W = p.W, H = p.H, K = p.K;
   const int S = g.stages;                        // power of two
-  const uint32_t smask = static_cast<uint32_t>(S - 1);
-  const int sshift = g.stage_shift;
 
   // shared carve-up: ring | worklists | hist[kNBuf] | list[kNBuf] | per finisher warp: finA (also the emit scratch), finB
   unsigned char* ring = smem;
@@ -709,6 +708,8 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
   // Counters that run through both passes (pass 0: every item of this CTA; pass 1: the items whose speculative start
   // threshold turned out too high, redone without speculation).
   uint32_t gq = 0;     // chunks so far (producer / A / B)
+  uint32_t ring_s = 0, ring_ph = 0;   // ... and the ring stage / barrier phase parity of chunk gq (any number of stages)
+  auto ring_advance = [&]() { if (++ring_s == static_cast<uint32_t>(S)) { ring_s = 0u; ring_ph ^= 1u; } };
   uint32_t k = 0;      // items so far (A / B / finishers)
   uint32_t my_ticket = 0;   // finisher warps: ordinal of the item this warp finishes next
   int trace_n = 0;
@@ -733,11 +734,11 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
           if (pass == 1 && __ldcg(&p.retry[ii.item]) == 0u) continue;
           const ItemInfo it = decode_item(p, g, ii, static_cast<int>(sizeof(T)));
           int qq = 0, pli = 0;                          // chunk within the plane, plane within the item
-          for (int q = 0; q < it.nchunks; ++q, ++gq) {
-            const uint32_t s = gq & smask;
+          for (int q = 0; q < it.nchunks; ++q, ++gq, ring_advance()) {
+            const uint32_t s = ring_s;
             if (gq >= static_cast<uint32_t>(S)) {
               const long long w0 = RTM3D_CLK();
-              pl::mbar_wait(pl::smem_u32(&ctl.empty[s]), ((gq >> sshift) - 1u) & 1u, p.status, 0xE1000001u, 64);
+              pl::mbar_wait(pl::smem_u32(&ctl.empty[s]), ring_ph ^ 1u, p.status, 0xE1000001u, 64);
               RTM3D_ACC(kStProdWait, RTM3D_CLK() - w0);
             }
             const int c_lo = it.ys + qq * g.chunk_rows, c_hi = min(c_lo + g.chunk_rows, it.ye);
@@ -786,15 +787,15 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
         t_floor = fmaxf(t_floor, L.spec_t);
         if (lane == 0) RTM3D_ACC(kStASetup, RTM3D_CLK() - as0);
         int qq = 0;                                     // chunk within the plane
-        for (int q = 0; q < it.nchunks; ++q, ++gq) {
-          const uint32_t s = gq & smask;
+        for (int q = 0; q < it.nchunks; ++q, ++gq, ring_advance()) {
+          const uint32_t s = ring_s;
           if ((gq & (kAGroups - 1)) != static_cast<uint32_t>((warp - kAWarp0) / kAPerGroup)) {   // the other group's chunk
             if (++qq == it.cpp) qq = 0;
             continue;
           }
           {
             const long long w0 = RTM3D_CLK();
-            pl::mbar_wait(pl::smem_u32(&ctl.full[s]), (gq >> sshift) & 1u, p.status, 0xE1000002u, 100);
+            pl::mbar_wait(pl::smem_u32(&ctl.full[s]), ring_ph, p.status, 0xE1000002u, 100);
             if (lane == 0) RTM3D_MARK(1 + (warp - kAWarp0) % kAPerGroup, gq);
             if (lane == 0) RTM3D_ACC(kStWaitFull, RTM3D_CLK() - w0);
           }
@@ -870,11 +871,11 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
         t_floor = fmaxf(t_floor, L.spec_t);
         int qq = 0;                                     // chunk within the plane
         uint32_t flat_base = it.flat_base;              // of the plane the chunk belongs to
-        for (int q = 0; q < it.nchunks; ++q, ++gq) {
-          const uint32_t s = gq & smask;
+        for (int q = 0; q < it.nchunks; ++q, ++gq, ring_advance()) {
+          const uint32_t s = ring_s;
           {
             const long long w0 = RTM3D_CLK();
-            pl::mbar_wait(pl::smem_u32(&ctl.scanned[s]), (gq >> sshift) & 1u, p.status, 0xE1000005u, 100);
+            pl::mbar_wait(pl::smem_u32(&ctl.scanned[s]), ring_ph, p.status, 0xE1000005u, 100);
             if (lane == 0) RTM3D_MARK(10 + (warp - kBWarp0), gq);
             if (lane == 0) RTM3D_ACC(kStWaitScanned, RTM3D_CLK() - w0);
           }
@@ -1248,10 +1249,11 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
 // ---------------------------------------------------------------------------------------------------------------
 static int g_sm_count = 0;
 static unsigned long long* g_stats = nullptr;
+static int g_stages_override = 0;
 static unsigned long long* g_trace = nullptr;
 void debug_set_trace(unsigned long long* t) { g_trace = t; }
 static int g_copy_rows = 0;   // developer knob (debug_set_copy_rows): rows per bulk copy, 0 = whole chunk
-void debug_set_copy_rows(int r) { g_copy_rows = r; }
+void debug_set_copy_rows(int r) { if (r >= 1000) { g_stages_override = r - 1000; g_copy_rows = 0; } else g_copy_rows = r; }
 void debug_set_stats(unsigned long long* dev_u64_16) { g_stats = dev_u64_16; }
 
 static bool make_plane_geom(const PlaneParams& p, int dtype, int split_override, int speculate, PlaneGeom& g) {
@@ -1305,16 +1307,16 @@ static bool make_plane_geom(const PlaneParams& p, int dtype, int split_override,
   const size_t budget = 220 * 1024;
   if (fixed + 2ull * 3 * row_bytes > budget) return false;
   const int strip = (p.H + split - 1) / split;
-  // ring: up to 4 stages of ~32 KB (+ a 2-byte worklist slot per 16-byte centre group); fewer / smaller stages when the
-  // selection buffers are large
-  int stages = kMaxStages;
+  // ring: kDefaultStages stages sharing ~144 KB (+ a 2-byte worklist slot per 16-byte centre group); smaller stages
+  // when the selection buffers are large
+  int stages = g_stages_override > 0 ? g_stages_override : kDefaultStages;
   const size_t ring = budget - fixed;
   auto rows_for = [&](int st) {
     const long long per_stage = static_cast<long long>(ring / st) - 2LL * row_bytes - 64 - 2LL * kAPerGroup * 64;
     return static_cast<int>(per_stage * 8 / (9LL * row_bytes));       // cr*row_bytes + cr*row_bytes/8 <= per_stage
   };
   int cr = rows_for(stages);
-  const int cr_target = 36864 / row_bytes - 2;
+  const int cr_target = (36864 * 4 / stages) / row_bytes - 2;
   if (cr > cr_target && cr_target >= 1) cr = cr_target;
   if (cr < 1) { stages = 2; cr = rows_for(stages); }
   if (cr < 1) return false;
@@ -1326,7 +1328,6 @@ static bool make_plane_geom(const PlaneParams& p, int dtype, int split_override,
   g.nch_lo = (g.rows_lo + cr - 1) / cr;
   g.nch_hi = (g.rows_lo + 1 + cr - 1) / cr;
   g.stages = stages;
-  g.stage_shift = stages == 4 ? 2 : 1;
   g.speculate = speculate;
   g.chunk_rows = cr;
   g.copy_rows = g_copy_rows > 0 ? g_copy_rows : cr + 2;
