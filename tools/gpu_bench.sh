@@ -10,10 +10,10 @@ print("$wl", d["value"], "img/s", d["ms_per_step"], "ms/step", d["roofline"]["ke
 PY
 done
 if [ "$2" == "ncu" ]; then
-python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/plain_$TAG.log 2>&1 &&
+python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_$TAG.csv \
-    python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches_$TAG.log 2>&1; echo "ncu launches rc=$?"
-python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/plain2_$TAG.log 2>&1 &&
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_launches_$TAG.log 2>&1; echo "ncu launches rc=$?"
+python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/plain2_$TAG.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:decode_planes -s 4 -c 1 -o gpurun_out/prof_$TAG -f \
-    python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
 fi
