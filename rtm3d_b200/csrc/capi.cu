@@ -91,6 +91,7 @@ int dispatch(rtm3d::DecodeParams& p, const rtm3d::WorkspaceLayout& L, int dtype,
     q.tickets = p.tickets; q.keys = p.keys; q.key_counts = p.key_counts; q.status = p.status;
     q.retry = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(p.tickets) - L.tickets_off + L.retry_off);
     q.guess = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(p.tickets) - L.tickets_off + L.guess_off);
+    q.ftable = reinterpret_cast<const float*>(reinterpret_cast<unsigned char*>(p.tickets) - L.tickets_off + L.table_off);
     if (main && !q.flat)   // the epilogue needs the flat indices even when the caller does not
       q.flat = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(p.tickets) - L.tickets_off + L.flat_off);
     const int rc = rtm3d::launch_planes(q, dtype, static_cast<int>((flags >> 8) & 0xFu), (flags & RTM3D_FLAG_NO_SPECULATION) ? 0 : 1,
@@ -135,7 +136,11 @@ int rtm3d_decode_workspace_bytes(int B, int C, int H, int W, int K, size_t* out_
 
 int rtm3d_workspace_init(void* ws, size_t ws_bytes, void* stream) {
   if (!ws) return fail(RTM3D_ERR_NULL, "ws is NULL");
-  return cuda_fail(static_cast<int>(cudaMemsetAsync(ws, 0, ws_bytes, static_cast<cudaStream_t>(stream))), "workspace memset");
+  if (int e = cuda_fail(static_cast<int>(cudaMemsetAsync(ws, 0, ws_bytes, static_cast<cudaStream_t>(stream))), "workspace memset")) return e;
+  // the logit bound of every histogram bin (double-precision log, once per workspace instead of inside the kernels)
+  if (ws_bytes >= static_cast<size_t>(rtm3d::kFilterTableWords) * 4)
+    return cuda_fail(rtm3d::launch_filter_table(static_cast<float*>(ws), static_cast<cudaStream_t>(stream)), "threshold table launch");
+  return 0;
 }
 
 int rtm3d_decode_main(const void* hm, const void* off, const void* off2, int dtype, int B, int C, int H, int W,
@@ -281,6 +286,7 @@ int rtm3d_decode_fused(const void* hm, const void* off, const void* off2, const 
     q.status = reinterpret_cast<uint32_t*>(base + L.status_off);
     q.retry = reinterpret_cast<uint32_t*>(base + L.retry_off);
     q.guess = reinterpret_cast<uint32_t*>(base + L.guess_off);
+    q.ftable = reinterpret_cast<const float*>(base + L.table_off);
     const int rc = rtm3d::launch_planes(q, dtype, static_cast<int>((flags >> 8) & 0xFu), (flags & RTM3D_FLAG_NO_SPECULATION) ? 0 : 1,
                                         static_cast<int>((flags >> 16) & 0xFFu), static_cast<int>((flags >> 24) & 0xFu), s);
     if (rc != -1000) {

@@ -140,6 +140,8 @@ WorkspaceLayout workspace_layout(int B, int C, int H, int W, int K) {
   L.list_cap = static_cast<int>(cap > 2L * K ? cap : 2L * K);
   L.generic_smem = generic_smem_bytes(W, K, L.strip_rows, L.list_cap);
   size_t off = 0;
+  L.table_off = off;                                 // fixed position: rtm3d_workspace_init fills it without knowing the shape
+  off += static_cast<size_t>(kFilterTableWords) * 4;
   L.tickets_off = off;
   off += ((static_cast<size_t>(B) * (C + 1) * 4 + 255) / 256) * 256;
   L.status_off = off;

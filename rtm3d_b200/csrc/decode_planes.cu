@@ -525,13 +525,19 @@ static __device__ __noinline__ void compact_list(Sel& L, unsigned long long* lis
   __syncwarp();
 }
 
+// filter_from_bin through the workspace's table when rtm3d_workspace_init has filled it (ft != nullptr)
+__device__ __forceinline__ float filter_lookup(const float* ft, int bin) {
+  if (bin < 1) return -INFINITY;
+  return ft ? __ldg(ft + bin) : filter_from_bin(bin);
+}
+
 // Re-derive the item's logit threshold from its histogram (caller holds L.lock, warp-converged).
-static __device__ __noinline__ void update_threshold(Sel& L, const uint32_t* hist, int K, int lane) {
+static __device__ __noinline__ void update_threshold(Sel& L, const uint32_t* hist, int K, int lane, const float* ft) {
   const uint32_t r = L.reserve;
   const int bin = warp_hist_boundary(hist, K, lane);
   if (lane == 0) {
     if (bin >= 0) {
-      const float t = filter_from_bin(bin);
+      const float t = filter_lookup(ft, bin);
       if (t > L.t_filter) L.t_filter = t;
     }
     L.last_bin = bin;
@@ -672,6 +678,8 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
   for (int i = tid; i < kNBuf * g.list_cap; i += kPlaneThreads) list_all[i] = 0ull;
   __syncthreads();
 
+  // the workspace's threshold table, if it is there (a workspace that was only zeroed falls back to computing the bounds)
+  const float* ftable = (p.ftable && __float_as_uint(__ldg(p.ftable + kFilterTableWords - 1)) == kFilterTableMagic) ? p.ftable : nullptr;
   const int planes_per_img = p.C + p.Cv;
   CtaItems cta_items;
   cta_items.init(p, g, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x));
@@ -695,7 +703,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
       if (item < g.n_items) {
         const int sb = spec_for_plane(item_plane(p, g, cta_items.n_main, item));
         ctl.sel[q].spec_bin = sb;
-        ctl.sel[q].spec_t = filter_from_bin(sb);
+        ctl.sel[q].spec_t = filter_lookup(ftable, sb);
       }
     }
   }
@@ -1010,7 +1018,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
             upd = __shfl_sync(0xffffffffu, upd, 0);
             if (upd) {
               if (lane == 0) RTM3D_ACC(kStUpdates, 1);
-              update_threshold(L, hist, K, lane);
+              update_threshold(L, hist, K, lane, ftable);
               __syncwarp();
               if (lane == 0) { __threadfence_block(); atomicExch(&L.lock, 0u); }
             }
@@ -1119,7 +1127,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
           const int nxt = cta_items.at(ii.kl + kNBuf);           // (pass 0 walks every item: kl == ord)
           if (g.speculate && pass == 0 && nxt < g.n_items) nsb = spec_for_plane(item_plane(p, g, cta_items.n_main, nxt));
           L.spec_bin = nsb;
-          L.spec_t = filter_from_bin(nsb);          // (-inf for nsb < 1)
+          L.spec_t = filter_lookup(ftable, nsb);    // (-inf for nsb < 1)
           __threadfence_block();
           ctl.fin_released[buf] = (ord >> kBufShift) + 1u;
           pl::mbar_arrive(pl::smem_u32(&ctl.buf_free[buf]));
@@ -1377,6 +1385,17 @@ __global__ void threshold_table_kernel(float* t, uint32_t* edge, int n) {
   if (bin >= n) return;
   t[bin] = filter_from_bin(bin);
   edge[bin] = bin >= 1 ? bin_edge_bits(bin) : 0u;
+}
+__global__ void filter_table_kernel(float* t) {
+  const int bin = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bin < kHistBins) t[bin] = bin >= 1 ? filter_from_bin(bin) : -INFINITY;
+  else if (bin < kFilterTableWords - 1) t[bin] = 15.0f;
+  else if (bin == kFilterTableWords - 1) t[bin] = __uint_as_float(kFilterTableMagic);
+}
+int launch_filter_table(float* table, cudaStream_t s) {
+  static_assert(kHistBins < kFilterTableWords, "table too small");
+  filter_table_kernel<<<kFilterTableWords / 128, 128, 0, s>>>(table);
+  return static_cast<int>(cudaGetLastError());
 }
 int threshold_table_bins() { return static_cast<int>((0x3F800000u >> kScoreShift) - kScoreBase) + 1; }
 int launch_threshold_table(float* t, uint32_t* edge, cudaStream_t s) {

@@ -49,12 +49,13 @@ struct PlaneParams {
   uint32_t* key_counts;  // [items]
   uint32_t* retry;       // [items] zero between calls: items to redo without speculation
   uint32_t* guess;       // [64] boundary bin + 1 remembered per plane index from the previous launch (0 = none)
+  const float* ftable;   // [kFilterTableWords] logit bound per histogram bin, written by rtm3d_workspace_init (last word = magic)
   uint32_t* status;      // watchdog word (0 = ok)
   unsigned long long* stats;  // developer counters (nullable; decode_planes.cu StatSlot)
 };
 
 struct WorkspaceLayout {
-  size_t tickets_off, status_off, keys_off, counts_off, retry_off, guess_off, flat_off, total;
+  size_t table_off, tickets_off, status_off, keys_off, counts_off, retry_off, guess_off, flat_off, total;
   int strip_rows, nstrips, list_cap;
   size_t generic_smem;
 };
@@ -69,6 +70,9 @@ int launch_generic(const DecodeParams& p, int dtype, int mode, size_t smem, cuda
 int launch_planes(const PlaneParams& p, int dtype, int split_override, int speculate, int max_ctas, int debug, cudaStream_t s);
 bool planes_eligible(const PlaneParams& p, int dtype);
 constexpr int kPlanesMaxSplit = 8;
+constexpr int kFilterTableWords = 2048;        // >= histogram bins + 1; the last word holds kFilterTableMagic
+constexpr unsigned kFilterTableMagic = 0x5A17AB1Eu;
+int launch_filter_table(float* table, cudaStream_t s);   // fills a workspace's table (rtm3d_workspace_init)
 int threshold_table_bins();
 void debug_set_stats(unsigned long long* dev_u64_16);
 void debug_set_trace(unsigned long long* dev_u64_960);
