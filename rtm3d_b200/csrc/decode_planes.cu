@@ -696,15 +696,14 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
     }
     return gb > kSpecMargin ? gb - kSpecMargin : -1;
   };
-  if (tid == 0 && g.speculate) {
+  if (tid < kNBuf && g.speculate) {
     // the first items of this CTA start from what the previous launch remembered
-    for (int q = 0; q < kNBuf; ++q) {
-      const int item = cta_items.at(q);
-      if (item < g.n_items) {
-        const int sb = spec_for_plane(item_plane(p, g, cta_items.n_main, item));
-        ctl.sel[q].spec_bin = sb;
-        ctl.sel[q].spec_t = filter_lookup(ftable, sb);
-      }
+    const int q = tid;
+    const int item = cta_items.at(q);
+    if (item < g.n_items) {
+      const int sb = spec_for_plane(item_plane(p, g, cta_items.n_main, item));
+      ctl.sel[q].spec_bin = sb;
+      ctl.sel[q].spec_t = filter_lookup(ftable, sb);
     }
   }
   __syncthreads();
@@ -726,8 +725,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
   if (!STATS && p.stats && tid == 0) p.stats[3840 + 4 * blockIdx.x + 1] = pl::globaltimer_ns();
   for (int pass = 0; pass < 2; ++pass) {
     if (pass == 1) {
-      __threadfence();
-      __syncthreads();               // every role is done with pass 0; the retry flags are visible
+      __syncthreads();               // every role is done with pass 0; the retry flags (this CTA's own writes) are visible
       if (!STATS && p.stats && tid == 0) p.stats[3840 + 4 * blockIdx.x + 2] = pl::globaltimer_ns();
       if (ctl.n_retry == 0u) break;  // (nearly always)
     }

@@ -239,3 +239,22 @@ def test_pack_wire_kernel_matches_torch_packing():
     back = PackedDetections.from_wire(wire, 30)
     for f in ("cls", "score", "proj", "verts", "bbox", "flat", "counts"):
         assert torch.equal(getattr(back, f), getattr(det, f)), f
+
+
+def test_zeroed_workspace_without_threshold_table_gives_the_same_bits():
+    """rtm3d_workspace_init also writes the per-bin logit bounds; a workspace that was only zeroed (the pre-table
+    contract) makes the kernel compute the bounds itself.  Both must give the same result."""
+    logits, kpt = synth.head_outputs(4, 3, 96, 320, seed=77, kind="randn", kpt_channels=9)
+    dev_logits = [t.to(DEV) for t in logits]
+    dec = HeatmapDecoder(0.4, 50, 4.0)
+    first = dec.decode_packed(dev_logits)
+    cand = dec.decode_keypoints(kpt.to(DEV), dev_logits[3])
+    torch.cuda.synchronize()
+    for ws in dec._ws.values():
+        ws.zero_()                       # erases the table (and the remembered thresholds)
+    again = dec.decode_packed(dev_logits)
+    cand2 = dec.decode_keypoints(kpt.to(DEV), dev_logits[3])
+    torch.cuda.synchronize()
+    for f in ("cls", "score", "proj", "verts", "bbox", "flat", "counts"):
+        assert torch.equal(getattr(first, f), getattr(again, f)), f
+    assert torch.equal(cand.flat, cand2.flat) and torch.equal(cand.score, cand2.score)
