@@ -1242,7 +1242,9 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
   // leave the workspace clean: clear this CTA's retry flags once every role has finished reading them
   __syncthreads();
   if (!STATS && p.stats && tid == 0) p.stats[3840 + 4 * blockIdx.x + 3] = pl::globaltimer_ns();
-  if (blockIdx.x == 0 && tid < kMaxPlanes && ctl.guess_bin[tid] >= 0) p.guess[tid] = static_cast<uint32_t>(ctl.guess_bin[tid] + 1);
+  // remember the boundaries for the next launch.  Every CTA writes the planes it has seen (a CTA of a small batch sees
+  // only a few plane indices); CTAs that disagree race benignly -- any of their values is a valid starting guess.
+  if (tid < kMaxPlanes && ctl.guess_bin[tid] >= 0) p.guess[tid] = static_cast<uint32_t>(ctl.guess_bin[tid] + 1);
 #pragma unroll 1
   if (ctl.n_retry != 0u) {
     for (int kl = tid; kl < cta_items.count; kl += kPlaneThreads) {
@@ -1278,18 +1280,17 @@ static bool make_plane_geom(const PlaneParams& p, int dtype, int split_override,
     g_sm_count = n;
   }
   const long long planes = static_cast<long long>(p.B) * ((p.C > 0 ? 1 : 0) + p.Cv);   // items per strip index (the C main planes are one item)
-  // strips per plane: enough items to fill the chip and a last wave that is not mostly idle
+  // Strips per plane.  Splitting a selection problem over several CTAs costs a publish + merge through global memory on
+  // the finisher warps, which are the busiest part of a CTA: measured, split = 1 is never slower for batches of 1..256
+  // images of 96x320 or 192x640 planes (tools/split_time.py), and 2-15x faster once there are more items than SMs.
+  // Only a handful of very large planes (>= 1 MB per strip, fewer items than a quarter of the SMs) are cut into strips.
   int split = 1;
   if (split_override > 0) {
     split = split_override;
   } else {
-    while (split < 8 && p.H / (2 * split) >= 8) {
-      const double waves = static_cast<double>(planes * split) / g_sm_count;
-      const double eff = waves / static_cast<double>(static_cast<long long>(waves + 0.999999));
-      if (planes * split >= 2LL * g_sm_count && eff >= 0.9) break;
-      if (planes * split >= 4LL * g_sm_count) break;
+    while (split < 8 && p.H / (2 * split) >= 8 && planes * split * 4 <= g_sm_count &&
+           static_cast<long long>(p.H) * row_bytes / split >= (1LL << 20))
       split *= 2;
-    }
   }
   while (split > 1 && p.H < split) split /= 2;
   const int max_parts = split;
