@@ -630,7 +630,8 @@ static __device__ __noinline__ void warp_write_kpt(const PlaneParams& p, int b, 
 
 // DBG: the timing experiments of PlaneGeom::debug are compiled in (tools/debug_time.py); the production instantiation
 // carries none of their tests -- every instruction on a role's per-chunk path counts.
-template <typename T, bool STATS, bool DBG>
+// SPLIT: planes are cut into strips (the publish + merge path of the finishers is compiled in).
+template <typename T, bool STATS, bool DBG, bool SPLIT>
 __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const PlaneParams p, const PlaneGeom g) {
   const int dbg = DBG ? g.debug : 0;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -1149,7 +1150,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
         if (dbg == 5) continue;
 
         // ---- emit, or publish + merge by the last part of the problem
-        const int parts = g.split;                     // strips of the problem (image, or keypoint plane)
+        const int parts = SPLIT ? g.split : 1;         // strips of the problem (image, or keypoint plane)
         const int kc = it.kc;
         bool do_emit = true;
         if (parts > 1) {
@@ -1355,9 +1356,9 @@ bool planes_eligible(const PlaneParams& p, int dtype) {
   return make_plane_geom(p, dtype, 0, 1, g);
 }
 
-template <typename T, bool STATS, bool DBG>
+template <typename T, bool STATS, bool DBG, bool SPLIT>
 static int launch_planes_t(const PlaneParams& p, const PlaneGeom& g, cudaStream_t s) {
-  auto kern = decode_planes_kernel<T, STATS, DBG>;
+  auto kern = decode_planes_kernel<T, STATS, DBG, SPLIT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   int grid = g.n_items < g_sm_count ? g.n_items : g_sm_count;
@@ -1373,9 +1374,10 @@ int launch_planes(const PlaneParams& p, int dtype, int split_override, int specu
   g.debug = debug;
   PlaneParams q = p;
   q.stats = g_stats ? g_stats : g_trace;
-  if (g_stats) return dtype == 0 ? launch_planes_t<float, true, false>(q, g, s) : launch_planes_t<__nv_bfloat16, true, false>(q, g, s);
-  if (debug != 0) return dtype == 0 ? launch_planes_t<float, false, true>(q, g, s) : launch_planes_t<__nv_bfloat16, false, true>(q, g, s);
-  return dtype == 0 ? launch_planes_t<float, false, false>(q, g, s) : launch_planes_t<__nv_bfloat16, false, false>(q, g, s);
+  if (g_stats) return dtype == 0 ? launch_planes_t<float, true, false, true>(q, g, s) : launch_planes_t<__nv_bfloat16, true, false, true>(q, g, s);
+  if (debug != 0) return dtype == 0 ? launch_planes_t<float, false, true, true>(q, g, s) : launch_planes_t<__nv_bfloat16, false, true, true>(q, g, s);
+  if (g.split > 1) return dtype == 0 ? launch_planes_t<float, false, false, true>(q, g, s) : launch_planes_t<__nv_bfloat16, false, false, true>(q, g, s);
+  return dtype == 0 ? launch_planes_t<float, false, false, false>(q, g, s) : launch_planes_t<__nv_bfloat16, false, false, false>(q, g, s);
 }
 
 // Verification aid: the logit threshold and the score edge of every histogram bin (rtm3d_threshold_table).
