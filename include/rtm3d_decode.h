@@ -59,9 +59,12 @@ const char* rtm3d_last_error(void);
 /* static string: compiler, arch and kernel variants built in */
 const char* rtm3d_build_info(void);
 
-/* Bytes of device scratch the decode entry points need for this shape (keys of the per-strip top-K lists and the
- * per-image tickets).  The scratch must be zeroed ONCE with rtm3d_workspace_init after allocation; every call leaves
- * it clean again (tickets are reset by the CTA that consumes them). */
+/* Bytes of device scratch the decode entry points need for this shape (the threshold table, keys of the per-strip
+ * top-K lists, per-image tickets, remembered thresholds).  The scratch must be initialised ONCE with
+ * rtm3d_workspace_init after allocation (zero fill + the table of logit bounds per score-histogram bin, 8 KB at the
+ * start of the scratch); every call leaves it clean again (tickets are reset by the CTA that consumes them).  A scratch
+ * that was only zeroed still gives identical results -- the kernels then compute the bounds themselves, more slowly.
+ * After a call that returned a CUDA error the scratch must be initialised again. */
 int rtm3d_decode_workspace_bytes(int B, int C, int H, int W, int K, size_t* out_bytes);
 int rtm3d_workspace_init(void* ws, size_t ws_bytes, void* stream);
 
