@@ -207,7 +207,10 @@ def run_b200(args, w):
         dist.init_process_group("nccl", device_id=dev)
 
     K, B, Cv = w["K"], w["B"], w["kpt"]
-    dec = HeatmapDecoder(THRESH, K, DOWN)
+    # N > 1: the all-gather's NCCL kernel runs beside the next batch's decode; the persistent plane kernel leaves it a few
+    # SMs instead of queueing its last CTAs behind it (--max-ctas; 0 = one CTA per SM)
+    max_ctas = args.max_ctas if args.max_ctas >= 0 else (0 if world == 1 else 144)
+    dec = HeatmapDecoder(THRESH, K, DOWN, max_ctas=max_ctas)
     nsets = 2
     sets = [make_inputs(torch, w, dev, 1234 + rank + 100 * s) for s in range(nsets)]
     heat_bytes = B * (w["C"] + Cv) * w["H"] * w["W"] * 4
@@ -374,6 +377,7 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg4")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="device-resident timed loop only (the ncu passes)")
+    ap.add_argument("--max-ctas", type=int, default=-1, help="CTAs of the plane-streaming kernel (-1: all SMs at N=1, 144 at N>1)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
