@@ -126,11 +126,13 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(n for b, n in self.REASONS.items() if bits & b)}
 
 
-def make_inputs(torch, w, device, seed, kind="randn"):
-    """every head map torch.randn from a seeded generator on the owning device."""
+def make_inputs(torch, w, device, seed, kind="randn", dtype="f32"):
+    """every head map torch.randn from a seeded generator on the owning device.  dtype "bf16": the maps as
+    a bf16-emitting head would hand them over; the decode widens them exactly and computes in fp32."""
     g = torch.Generator(device=device).manual_seed(seed)
     B, C, H, W = w["B"], w["C"], w["H"], w["W"]
-    mk = lambda c: torch.randn((B, c, H, W), generator=g, device=device, dtype=torch.float32)
+    td = torch.bfloat16 if dtype == "bf16" else torch.float32
+    mk = lambda c: torch.randn((B, c, H, W), generator=g, device=device, dtype=torch.float32).to(td)
     logits = [mk(C), mk(16), mk(2), mk(2)]
     kpt = mk(w["kpt"]) if w["kpt"] else None
     return logits, kpt
@@ -210,10 +212,11 @@ def run_b200(args, w):
     # N > 1: the all-gather's NCCL kernel runs beside the next batch's decode; the persistent plane kernel leaves it a few
     # SMs instead of queueing its last CTAs behind it (--max-ctas; 0 = one CTA per SM)
     max_ctas = args.max_ctas if args.max_ctas >= 0 else (0 if world == 1 else 144)
-    dec = HeatmapDecoder(THRESH, K, DOWN, max_ctas=max_ctas)
+    dec = HeatmapDecoder(THRESH, K, DOWN, max_ctas=max_ctas, reuse_outputs=(world == 1))   # N > 1: results stay referenced while they are gathered
     nsets = 2
-    sets = [make_inputs(torch, w, dev, 1234 + rank + 100 * s) for s in range(nsets)]
-    heat_bytes = B * (w["C"] + Cv) * w["H"] * w["W"] * 4
+    sets = [make_inputs(torch, w, dev, 1234 + rank + 100 * s, dtype=args.dtype) for s in range(nsets)]
+    elem = 2 if args.dtype == "bf16" else 4
+    heat_bytes = B * (w["C"] + Cv) * w["H"] * w["W"] * elem
     # kernels per step: plane-streaming kernel + fused post kernel (main only: + Tier A epilogue)
     launches_per_step = 2 + (1 if world > 1 else 0)    # + the wire-packing kernel of the gather
     marks_per_step = 3 if Cv else 2          # events: before, after the plane kernel, after the post kernel
@@ -297,7 +300,7 @@ def run_b200(args, w):
         host_kpt = sets[0][1].to("cpu").pin_memory() if Cv else None
         depth = 2
         decs = [HeatmapDecoder(THRESH, K, DOWN) for _ in range(depth)]
-        sess = [HostDecodeSession(d, B, w["C"], w["H"], w["W"], n_vert=8, kpt_channels=Cv, device=dev) for d in decs]
+        sess = [HostDecodeSession(d, B, w["C"], w["H"], w["W"], n_vert=8, kpt_channels=Cv, dtype=sets[0][0][0].dtype, device=dev) for d in decs]
         streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
         e2e_steps = max(4, min(args.steps, 20))
 
@@ -332,7 +335,7 @@ def run_b200(args, w):
 
     if rank == 0:
         peak, peak_src = peaks()
-        A, A_main, A_kpt = algorithmic_bytes_per_image(w)
+        A, A_main, A_kpt = algorithmic_bytes_per_image(w, elem=elem)
         dom = max(kernel_ms, key=kernel_ms.get)
         dom_bytes = B * (A if dom.startswith("decode_planes(main+kpt)") else A_main if dom.startswith("decode_planes") else 0)
         achieved = dom_bytes / (kernel_ms[dom] * 1e-3) / 1e9 if kernel_ms[dom] > 0 else 0.0
@@ -340,7 +343,7 @@ def run_b200(args, w):
         line = {
             "metric": METRIC, "value": round(B * world / (ms_step * 1e-3), 1), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 5), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if elem == 4 else "f32 (bf16 maps widened on load)", "data": "synthetic",
             "config": dict(config_dict(args.workload, w, world),
                            l2=f"{nsets} input sets rotated, {heat_bytes / 1e6:.0f} MB of heat-map per step vs 126 MB L2"
                               + ("" if heat_bytes > 130e6 else " (SMALLER than L2: later steps may hit L2)")),
@@ -376,6 +379,7 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg4")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dtype", choices=["f32", "bf16"], default="f32", help="element type of the head maps handed to the decode")
     ap.add_argument("--no-e2e", action="store_true", help="device-resident timed loop only (the ncu passes)")
     ap.add_argument("--max-ctas", type=int, default=-1, help="CTAs of the plane-streaming kernel (-1: all SMs at N=1, 144 at N>1)")
     args = ap.parse_args()

@@ -258,3 +258,21 @@ def test_zeroed_workspace_without_threshold_table_gives_the_same_bits():
     for f in ("cls", "score", "proj", "verts", "bbox", "flat", "counts"):
         assert torch.equal(getattr(first, f), getattr(again, f)), f
     assert torch.equal(cand.flat, cand2.flat) and torch.equal(cand.score, cand2.score)
+
+
+def test_reuse_outputs_returns_the_same_buffers_with_the_same_bits():
+    logits, kpt = synth.head_outputs(3, 3, 48, 80, seed=5, kind="randn", kpt_channels=9)
+    dev_logits = [t.to(DEV) for t in logits]
+    ref = HeatmapDecoder(0.4, 30, 4.0).decode_with_keypoints(dev_logits, kpt.to(DEV))
+    dec = HeatmapDecoder(0.4, 30, 4.0, reuse_outputs=True)
+    a = dec.decode_with_keypoints(dev_logits, kpt.to(DEV))
+    b = dec.decode_with_keypoints(dev_logits, kpt.to(DEV))
+    torch.cuda.synchronize()
+    assert a[0].score.data_ptr() == b[0].score.data_ptr() and a[2].kpt_j.data_ptr() == b[2].kpt_j.data_ptr()
+    for f in ("cls", "score", "proj", "verts", "bbox", "flat", "counts"):
+        assert torch.equal(getattr(ref[0], f), getattr(b[0], f)), f
+    for f in ("kpt_proj", "kpt_score", "kpt_j", "verts"):
+        assert torch.equal(getattr(ref[2], f), getattr(b[2], f)), f
+    p1 = dec.decode_packed(dev_logits)
+    p2 = dec.decode_packed(dev_logits)
+    assert p1.flat.data_ptr() == p2.flat.data_ptr() and torch.equal(p2.flat, ref[0].flat)
