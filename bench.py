@@ -212,7 +212,10 @@ def run_b200(args, w):
     # N > 1: the all-gather's NCCL kernel runs beside the next batch's decode; the persistent plane kernel leaves it a few
     # SMs instead of queueing its last CTAs behind it (--max-ctas; 0 = one CTA per SM)
     max_ctas = args.max_ctas if args.max_ctas >= 0 else (0 if world == 1 else 144)
-    dec = HeatmapDecoder(THRESH, K, DOWN, max_ctas=max_ctas, reuse_outputs=(world == 1))   # N > 1: results stay referenced while they are gathered
+    # result buffers are reused from call to call (saves ~35 us of host time per step); at N > 1 two decoders alternate so
+    # that a batch's results stay untouched while the gather stream packs them
+    decs_dev = [HeatmapDecoder(THRESH, K, DOWN, max_ctas=max_ctas, reuse_outputs=True) for _ in range(1 if world == 1 else 2)]
+    dec = decs_dev[0]
     nsets = 2
     sets = [make_inputs(torch, w, dev, 1234 + rank + 100 * s, dtype=args.dtype) for s in range(nsets)]
     elem = 2 if args.dtype == "bf16" else 4
@@ -224,7 +227,11 @@ def run_b200(args, w):
     gather_out = None
 
     def step(i, marks=None):
+        nonlocal gather_out
         logits, kpt = sets[i % nsets]
+        dec = decs_dev[i % len(decs_dev)]
+        if world > 1 and gather_out is not None and gather_out["packed"][i & 1] is not None:
+            torch.cuda.current_stream().wait_event(gather_out["packed"][i & 1])      # batch i-2's results have been packed
         if Cv:
             det, cand, grp = dec.decode_with_keypoints(logits, kpt, marks=marks)
         else:
@@ -238,10 +245,9 @@ def run_b200(args, w):
             # the path's one collective: pack (one launch of the library) + all-gather of the fixed-size
             # detections.  It runs on a second stream behind an event, so the gather of batch i overlaps the decode of
             # batch i+1; the timed region ends with a device-wide synchronise, i.e. with every gather complete.
-            nonlocal gather_out
             if gather_out is None:
                 per = K * PackedDetections.WORDS + 1
-                gather_out = dict(stream=torch.cuda.Stream(device=dev), keep=[None, None],
+                gather_out = dict(stream=torch.cuda.Stream(device=dev), packed=[None, None],
                                   full=[torch.empty((world * B, per), dtype=torch.int32, device=dev) for _ in range(2)],
                                   mine=[torch.empty((B, per), dtype=torch.int32, device=dev) for _ in range(2)])
             slot = i & 1
@@ -249,8 +255,11 @@ def run_b200(args, w):
             ready.record()
             with torch.cuda.stream(gather_out["stream"]):
                 gather_out["stream"].wait_event(ready)
-                dist.all_gather_into_tensor(gather_out["full"][slot], det.to_wire(gather_out["mine"][slot]))
-            gather_out["keep"][slot] = det          # the result buffers stay referenced until their gather has been issued twice over
+                wire = det.to_wire(gather_out["mine"][slot])
+                if gather_out["packed"][slot] is None:
+                    gather_out["packed"][slot] = torch.cuda.Event()
+                gather_out["packed"][slot].record()
+                dist.all_gather_into_tensor(gather_out["full"][slot], wire)
         return det, grp
 
     def barrier():
