@@ -25,10 +25,11 @@ if os.path.exists(lc):
     with open(os.path.join(pr, f"{tag}_launches.csv"), "w") as f:
         f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)\n")
         f.write("# share_of_rtm3d = share among this repo's kernels (torch's randn input generation excluded)\n")
-        f.write("kernel,grid,block,launches,mean_us,share_of_all,share_of_rtm3d\n")
+        f.write("# median_us: the first launch on a fresh workspace has no remembered thresholds and runs cold (~4x)\n")
+        f.write("kernel,grid,block,launches,mean_us,median_us,share_of_all,share_of_rtm3d\n")
         for (k, g, b), v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
             s_m = sum(v) / mine if "rtm3d::" in k and mine else 0.0
-            f.write(f"\"{k[:110]}\",\"{g}\",\"{b}\",{len(v)},{sum(v) / len(v) / 1e3:.2f},{sum(v) / tot:.4f},{s_m:.4f}\n")
+            f.write(f"\"{k[:110]}\",\"{g}\",\"{b}\",{len(v)},{sum(v) / len(v) / 1e3:.2f},{sorted(v)[len(v) // 2] / 1e3:.2f},{sum(v) / tot:.4f},{s_m:.4f}\n")
     print(open(os.path.join(pr, f"{tag}_launches.csv")).read())
 
 rep = os.path.join(go, f"prof_{tag}.ncu-rep")
