@@ -53,6 +53,8 @@ enum rtm3d_error {
                                    caller runs rtm3d_epilogue_main / rtm3d_epilogue_keypoints itself */
 #define RTM3D_FLAG_MAX_CTAS(n) (((unsigned)(n) & 0xFFu) << 16) /* plane-streaming kernel: at most n CTAs (0 = one per SM) */
 #define RTM3D_FLAG_SPLIT(s) (((unsigned)(s) & 0xFu) << 8) /* plane-streaming kernel: force s strips (1,2,4,8) per plane; 0 = auto */
+/* bits 24..27: developer timing experiments of the plane-streaming kernel (tools/debug_time.py; results are then WRONG);
+ * must be 0 in production.  The rtm3d_debug_* symbols the library also exports are developer instrumentation, not ABI. */
 
 int rtm3d_abi_version(void);
 const char* rtm3d_last_error(void);
