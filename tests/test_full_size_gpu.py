@@ -77,6 +77,11 @@ def test_full_size_properties_and_spot_checks(shape):
     _same(det, det3, fa); _same(cand, cand3, fb); _same(grp, grp3, fg)
     det4, cand4, grp4 = HeatmapDecoder(0.4, K, 4.0).decode_with_keypoints(logits, kpt, fused=False)
     _same(det, det4, fa); _same(cand, cand4, fb); _same(grp, grp4, fg)
+    # fewer CTAs than SMs (bench.py at N > 1 leaves four SMs to NCCL), strips (the publish + merge path), reused result buffers
+    det6, cand6, grp6 = HeatmapDecoder(0.4, K, 4.0, max_ctas=144, reuse_outputs=True).decode_with_keypoints(logits, kpt)
+    _same(det, det6, fa); _same(cand, cand6, fb); _same(grp, grp6, fg)
+    det7, cand7, grp7 = HeatmapDecoder(0.4, K, 4.0, split=2).decode_with_keypoints(logits, kpt)
+    _same(det, det7, fa); _same(cand, cand7, fb); _same(grp, grp7, fg)
     if B * H * W <= 256 * 96 * 320:                            # the generic kernels are slow: cfg4 only
         det5, cand5, grp5 = HeatmapDecoder(0.4, K, 4.0, force_generic=True).decode_with_keypoints(logits, kpt)
         _same(det, det5, fa); _same(cand, cand5, fb); _same(grp, grp5, fg)
