@@ -310,11 +310,12 @@ int rtm3d_decode_fused(const void* hm, const void* off, const void* off2, const 
     // the two calls carve the workspace for different plane counts: what the first one left in the region the second
     // one uses for its tickets must be cleared (each call leaves its OWN tickets clean)
     const rtm3d::WorkspaceLayout Lk = rtm3d::workspace_layout(B, Cv, H, W, K);
-    if (int e = cuda_fail(static_cast<int>(cudaMemsetAsync(ws, 0, Lk.status_off, s)), "workspace ticket reset")) return e;
+    // (tickets only: the threshold table in front of them is written once by rtm3d_workspace_init and must survive)
+    if (int e = cuda_fail(static_cast<int>(cudaMemsetAsync(static_cast<unsigned char*>(ws) + Lk.tickets_off, 0, Lk.status_off - Lk.tickets_off, s)), "workspace ticket reset")) return e;
     if (int e = rtm3d_decode_keypoints(kpt_hm, voff2, dtype, B, Cv, H, W, K, kscore, kxy, kflat, ws, ws_bytes, flags, stream))
       return e;
     const rtm3d::WorkspaceLayout Lm = rtm3d::workspace_layout(B, C, H, W, K);
-    if (int e = cuda_fail(static_cast<int>(cudaMemsetAsync(ws, 0, Lm.status_off, s)), "workspace ticket reset")) return e;
+    if (int e = cuda_fail(static_cast<int>(cudaMemsetAsync(static_cast<unsigned char*>(ws) + Lm.tickets_off, 0, Lm.status_off - Lm.tickets_off, s)), "workspace ticket reset")) return e;
   }
   if (flags & RTM3D_FLAG_NO_GROUP) return 0;
   return rtm3d_group_vertices(flat, counts, off, off2, dtype, B, H, W, n_vert, K, kscore, kxy, Cv, down, kpt_proj, kpt_score,

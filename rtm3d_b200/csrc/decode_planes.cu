@@ -39,6 +39,7 @@
 
 #include "common.cuh"
 #include "params.h"
+#include "scan_common.cuh"
 
 namespace rtm3d {
 
@@ -92,69 +93,6 @@ struct PlaneGeom {
   unsigned smem;
 };
 
-// ---------------------------------------------------------------------------------------------------------------
-// PTX wrappers
-namespace pl {
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// The heat-maps are read once: their lines are the first to leave L2 (`policy` = evict_first), which keeps the
-// selection outputs the post kernel reads next (score / flat / kflat) resident.
-__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
-  unsigned long long pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ unsigned long long l2_policy_evict_normal() {
-  unsigned long long pol;
-  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, unsigned long long policy) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar), "l"(policy)
-               : "memory");
-}
-__device__ __forceinline__ void fence_sc_cta() { asm volatile("fence.sc.cta;" ::: "memory"); }
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-// Bounded wait: a pipeline bug must surface as a launch failure, never as a hung GPU.  `backoff_ns`: sleep between
-// polls (waiting warps share issue slots with the scanners).
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t* status, uint32_t code, unsigned backoff_ns) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (true) {
-    __nanosleep(backoff_ns);
-    if (mbar_try_wait(bar, parity)) return;
-    if (clock64() - t0 > 4000000000LL) {
-      if (status) atomicExch(status, code);
-      __threadfence_system();
-      __trap();
-    }
-  }
-}
-}  // namespace pl
 
 // Developer counters (decode_planes_kernel<T, true> only; tools/plane_stats.py): summed over all CTAs of a launch.
 enum StatSlot { kStItems = 0, kStRetried, kStWlEntries, kStBatches, kStPushed, kStUpdates, kStCompactions, kStWaitBufFree,
@@ -438,50 +376,6 @@ __device__ __forceinline__ int count_greater(const unsigned long long* r, int le
 // ---------------------------------------------------------------------------------------------------------------
 // Scanner side.
 
-template <typename T> struct Grp;  // one 16-byte group of a row
-template <> struct Grp<float> {
-  static constexpr int E = 4;
-  __device__ static __forceinline__ void load(const unsigned char* p, float (&v)[4]) {
-    const float4 f = *reinterpret_cast<const float4*>(p);
-    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
-  }
-  __device__ static __forceinline__ float elem(const unsigned char* p, int i) { return reinterpret_cast<const float*>(p)[i]; }
-};
-template <> struct Grp<__nv_bfloat16> {
-  static constexpr int E = 8;
-  __device__ static __forceinline__ void load(const unsigned char* p, float (&v)[8]) {
-    const uint4 u = *reinterpret_cast<const uint4*>(p);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      v[2 * i] = __uint_as_float(w[i] << 16);
-      v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
-    }
-  }
-  __device__ static __forceinline__ float elem(const unsigned char* p, int i) {
-    return __uint_as_float(static_cast<uint32_t>(reinterpret_cast<const unsigned short*>(p)[i]) << 16);
-  }
-};
-
-// One row of the 3x3 window around a group: r[0] = left neighbour of the group's first pixel, r[1..E] = the pixels above /
-// below the group, r[E+1] = right neighbour of its last pixel; -inf where the image ends (max_pool2d's implicit padding).
-template <typename T>
-__device__ __forceinline__ void load_window_row(const unsigned char* p, bool has_row, bool has_l, bool has_r,
-                                                float (&r)[Grp<T>::E + 2]) {
-  constexpr int E = Grp<T>::E;
-  if (has_row) {
-    float v[E];
-    Grp<T>::load(p, v);
-#pragma unroll
-    for (int i = 0; i < E; ++i) r[i + 1] = v[i];
-    r[0] = has_l ? Grp<T>::elem(p, -1) : -INFINITY;
-    r[E + 1] = has_r ? Grp<T>::elem(p, E) : -INFINITY;
-  } else {
-#pragma unroll
-    for (int i = 0; i < E + 2; ++i) r[i] = -INFINITY;
-  }
-}
-
 // Compaction of a full list (caller holds L.lock, warp-converged, L.reserve >= cap so no new slot is handed out).
 static __device__ __noinline__ void compact_list(Sel& L, unsigned long long* list, int cap, int K, uint32_t* rsel, int lane) {
   // every slot below cap has an owner: wait until all of them are written (keys are non-zero)
@@ -672,7 +566,11 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
     ctl.n_retry = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (tid >= 64 && tid < 64 + kMaxPlanes) ctl.guess_bin[tid - 64] = static_cast<int>(__ldcg(&p.guess[tid - 64])) - 1;   // remembered from the previous launch
+  if (tid >= 64 && tid < 64 + kMaxPlanes) {
+    // remembered from the previous launch; anything that is not a bin number (a workspace reused with another shape) = none
+    const uint32_t gw = __ldcg(&p.guess[tid - 64]);
+    ctl.guess_bin[tid - 64] = gw <= static_cast<uint32_t>(kHistBins) ? static_cast<int>(gw) - 1 : -1;
+  }
 #pragma unroll 1
   for (int i = tid; i < kNBuf * kHistBins; i += kPlaneThreads) hist_all[i] = 0u;
 #pragma unroll 1
@@ -1348,7 +1246,8 @@ static bool make_plane_geom(const PlaneParams& p, int dtype, int split_override,
   }
   g.n_items = static_cast<int>(static_cast<long long>(p.B) * ((p.C > 0 ? 1 : 0) + p.Cv) * split);
   g.smem = static_cast<unsigned>(static_cast<size_t>(stages) * (g.stage_bytes + 2ull * g.wl_cap) + fixed);
-  return g.smem <= 227 * 1024 - 4096;
+  // dynamic + static shared memory (the control block and the parameter copy) must fit the 227 KB a block may use
+  return static_cast<size_t>(g.smem) + sizeof(PlaneCtl) + sizeof(PlaneParams) + 128 <= 232448;
 }
 
 bool planes_eligible(const PlaneParams& p, int dtype) {

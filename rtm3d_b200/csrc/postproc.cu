@@ -149,6 +149,7 @@ __global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kPostThread
   float2* peer_xy[kPostSplit];
 #pragma unroll
   for (int r = 0; r < kPostSplit; ++r) peer_xy[r] = reinterpret_cast<float2*>(cluster.map_shared_rank(s_xy, r));
+  cluster.sync();          // every CTA of the cluster has started: its shared memory may be written by its peers from here on
   for (int i = half * cand_per + tid; i < min(Cv * K, (half + 1) * cand_per); i += kPostThreads) {
     const size_t row = static_cast<size_t>(b) * Cv * K + i;
     const int flat = p.kflat[row];

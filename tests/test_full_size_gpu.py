@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 import torch
 
+import kpt_oracle
 import parity
 from oracle import decode_ref
 from rtm3d_b200 import HeatmapDecoder
@@ -68,6 +69,8 @@ def test_full_size_properties_and_spot_checks(shape):
             o = np.lexsort((vflat[c].cpu().numpy(), -vs[c].cpu().numpy().astype(np.float64)))
             assert np.array_equal(cand.flat[b, c].cpu().numpy(), vflat[c].cpu().numpy()[o]), f"image {b} channel {c}"
             assert np.array_equal(cand.score[b, c].cpu().numpy().view(np.uint32), vs[c].cpu().numpy()[o].view(np.uint32))
+        # the grouping of the same images (kpt_j / kpt_score / kpt_proj / verts, sub-pixel candidates) against the oracle
+        kpt_oracle.check_image(det, cand, grp, logits, kpt, b, K, what=f"full-size image {b}")
     # ---- idempotence across calls, speculation and kernel variants
     fa = ("cls", "score", "proj", "verts", "bbox", "flat", "counts")
     fb, fg = ("score", "xy", "flat"), ("kpt_proj", "kpt_score", "kpt_j", "verts")

@@ -5,6 +5,7 @@ import pytest
 import torch
 
 import golden_io
+import kpt_oracle
 import parity
 from oracle import decode_ref
 from rtm3d_b200 import HeatmapDecoder, synth
@@ -24,43 +25,8 @@ def _check(logits_cpu, kpt_cpu, K, variant, what):
     dec = HeatmapDecoder(0.4, K, 4.0, **variant)
     det, cand, grp = dec.decode_with_keypoints(logits, kpt, fused=fused)
     torch.cuda.synchronize()
-    B, Cv = kpt.shape[:2]
-    for b in range(B):
-        # candidates do not depend on the main branch
-        vs, vx, vy, vflat = decode_ref.keypoint_peaks(kpt[b], K)
-        for c in range(Cv):
-            # canonical order inside exact-score tie groups (CUDA topk already is; keep the comparison robust)
-            o = np.lexsort((vflat[c].cpu().numpy(), -vs[c].cpu().numpy().astype(np.float64)))
-            assert np.array_equal(cand.flat[b, c].cpu().numpy(), vflat[c].cpu().numpy()[o]), f"{what} b{b} c{c} kflat"
-            assert np.array_equal(cand.score[b, c].cpu().numpy().view(np.uint32),
-                                  vs[c].cpu().numpy()[o].view(np.uint32)), f"{what} b{b} c{c} kscore"
-        # grouping oracle on the CANONICALLY ordered candidates: torch.topk leaves the order inside exact-score tie
-        # groups implementation-defined (batched CUDA topk on short rows does not return them index-ascending), and
-        # argmin's "first minimal index" (models/model.py:151) depends on that order when two candidates are equidistant
-        cls, score, xf, yf, flat = decode_ref.main_peaks(logits[0][b], 0.4, K)
-        n = int(det.counts[b])
-        assert n == len(cls)
-        if n == 0:
-            continue
-        assert torch.equal(det.flat[b, :n].long(), flat)
-        order = torch.from_numpy(np.stack([np.lexsort((vflat[c].cpu().numpy(), -vs[c].cpu().numpy().astype(np.float64)))
-                                           for c in range(Cv)])).to(DEV)
-        vs_c, vx_c, vy_c = vs.gather(1, order), vx.gather(1, order), vy.gather(1, order)
-        vsub = torch.sigmoid(logits[3][b][:, vy_c.reshape(-1).long(), vx_c.reshape(-1).long()])
-        vx_c = (vx_c.reshape(-1) + vsub[0]).view(Cv, K)
-        vy_c = (vy_c.reshape(-1) + vsub[1]).view(Cv, K)
-        assert torch.equal(cand.xy[b, ..., 0], vx_c) and torch.equal(cand.xy[b, ..., 1], vy_c), f"{what} b{b} kxy"
-        off = decode_ref.vertex_offsets(logits[1][b], xf, yf)
-        sub = torch.sigmoid(logits[2][b][:, yf.long(), xf.long()])
-        mx, my = xf + sub[0], yf + sub[1]
-        if off.shape[0] < Cv:
-            off = torch.cat([off, off.new_zeros(Cv - off.shape[0], off.shape[1], 2)], dim=0)
-        kp, reg, ks, j = decode_ref.group_keypoints(mx, my, vx_c, vy_c, vs_c, off)
-        assert torch.equal(grp.kpt_j[b, :n].long(), j.t()), f"{what} b{b} kpt_j"
-        assert torch.equal(grp.kpt_score[b, :n], ks), f"{what} b{b} kpt_score"
-        assert torch.equal(grp.kpt_proj[b, :n], 4.0 * kp), f"{what} b{b} kpt_proj"
-        assert torch.equal(grp.verts[b, :n], 4.0 * reg), f"{what} b{b} verts"
-        assert torch.all(grp.kpt_j[b, n:] == -1)
+    for b in range(kpt.shape[0]):
+        kpt_oracle.check_image(det, cand, grp, logits, kpt, b, K, what=what)
 
 
 @pytest.mark.parametrize("variant", VARIANTS, ids=VARIANT_IDS)
