@@ -51,6 +51,8 @@ enum rtm3d_error {
 #define RTM3D_FLAG_NO_GROUP 4u /* rtm3d_decode_fused: stop after the two decodes (the caller runs rtm3d_group_vertices itself) */
 #define RTM3D_FLAG_NO_EPILOGUE 8u /* decode entry points: stop after the selection (score, flat, counts / kscore, kflat); the
                                    caller runs rtm3d_epilogue_main / rtm3d_epilogue_keypoints itself */
+#define RTM3D_FLAG_LEGACY_PLANES 16u /* use the round-1 plane-streaming kernel (histogram select inside the streaming CTA) instead of
+                                       the plane-resident scan kernel + select kernel */
 #define RTM3D_FLAG_MAX_CTAS(n) (((unsigned)(n) & 0xFFu) << 16) /* plane-streaming kernel: at most n CTAs (0 = one per SM) */
 #define RTM3D_FLAG_SPLIT(s) (((unsigned)(s) & 0xFu) << 8) /* plane-streaming kernel: force s strips (1,2,4,8) per plane; 0 = auto */
 /* bits 24..27: developer timing experiments of the plane-streaming kernel (tools/debug_time.py; results are then WRONG);

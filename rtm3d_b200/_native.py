@@ -7,7 +7,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librtm3d_decode.so")
+# (RTM3D_B200_LIB: developer override, e.g. the `make DEV=1` build with the instrumentation entry points)
+LIB_PATH = os.environ.get("RTM3D_B200_LIB") or os.path.join(_HERE, "librtm3d_decode.so")
 CSRC = os.path.join(_HERE, "csrc")
 ABI_VERSION = 1
 
@@ -16,6 +17,7 @@ FLAG_FORCE_GENERIC = 1
 FLAG_NO_SPECULATION = 2
 FLAG_NO_GROUP = 4
 FLAG_NO_EPILOGUE = 8
+FLAG_LEGACY_PLANES = 16
 
 _c = ctypes
 _vp, _i, _f, _sz, _u = _c.c_void_p, _c.c_int, _c.c_float, _c.c_size_t, _c.c_uint

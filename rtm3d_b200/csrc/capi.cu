@@ -74,6 +74,37 @@ int launch_epilogues(const rtm3d::PlaneParams& q, int dtype, unsigned flags, cud
   return 0;
 }
 
+
+// Plane-resident scan kernel + selection: writes score / flat / counts (C > 0) and kscore / kflat (Cv > 0).
+// Returns -1000 when the shape is not eligible for the scan kernel (the caller falls back).
+int scan_and_select(const rtm3d::PlaneParams& q, const rtm3d::WorkspaceLayout& L, void* ws, int dtype, unsigned flags, cudaStream_t s) {
+  unsigned char* base = static_cast<unsigned char*>(ws);
+  rtm3d::ScanParams sp{};
+  sp.hm_main = q.hm_main; sp.hm_kpt = q.hm_kpt;
+  sp.B = q.B; sp.C = q.C; sp.Cv = q.Cv; sp.H = q.H; sp.W = q.W; sp.K = q.K;
+  sp.thresh = q.thresh; sp.t0 = q.t0;
+  sp.cand = reinterpret_cast<unsigned long long*>(base + L.cand_off);
+  sp.cand_count = reinterpret_cast<uint32_t*>(base + L.cand_count_off);
+  sp.queue = reinterpret_cast<uint32_t*>(base + L.queue_off);
+  sp.status = q.status;
+#ifdef RTM3D_DEV
+  sp.stats = rtm3d::debug_get_stats();
+#else
+  sp.stats = nullptr;
+#endif
+  const int strips_override = static_cast<int>((flags >> 8) & 0xFu);
+  // the lists of this call must fit the workspace
+  const int sp_default = rtm3d::scan_strips_per_plane(q.H, q.W, q.K, dtype, strips_override);
+  if (sp_default <= 0 || static_cast<long long>(q.B) * (q.C + q.Cv) * sp_default > L.cand_strips || rtm3d::scan_list_cap(q.K) > L.cand_cap) return -1000;
+  if (rtm3d::select_smem_bytes(q.C, q.Cv, sp_default, rtm3d::scan_list_cap(q.K), q.K) > 200 * 1024) return -1000;
+  int Sp = 0, cap = 0;
+  const int rc = rtm3d::launch_scan(sp, dtype, strips_override, static_cast<int>((flags >> 16) & 0xFFu), static_cast<int>((flags >> 24) & 0xFu), s, &Sp, &cap);
+  if (rc == -1000) return rc;
+  if (int e = cuda_fail(rc, "decode (scan kernel) launch")) return e;
+  rtm3d::SelectParams sel{sp.cand, sp.cand_count, q.B, q.C, q.Cv, q.H, q.W, q.K, Sp, cap, q.thresh, q.score, q.flat, q.counts, q.kscore, q.kflat};
+  return cuda_fail(rtm3d::launch_select(sel, s), "decode (select kernel) launch");
+}
+
 int dispatch(rtm3d::DecodeParams& p, const rtm3d::WorkspaceLayout& L, int dtype, int mode, unsigned flags,
              cudaStream_t s) {
   if (!(flags & RTM3D_FLAG_FORCE_GENERIC)) {
@@ -94,12 +125,16 @@ int dispatch(rtm3d::DecodeParams& p, const rtm3d::WorkspaceLayout& L, int dtype,
     q.ftable = reinterpret_cast<const float*>(reinterpret_cast<unsigned char*>(p.tickets) - L.tickets_off + L.table_off);
     if (main && !q.flat)   // the epilogue needs the flat indices even when the caller does not
       q.flat = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(p.tickets) - L.tickets_off + L.flat_off);
-    const int rc = rtm3d::launch_planes(q, dtype, static_cast<int>((flags >> 8) & 0xFu), (flags & RTM3D_FLAG_NO_SPECULATION) ? 0 : 1,
-                                        static_cast<int>((flags >> 16) & 0xFFu), static_cast<int>((flags >> 24) & 0xFu), s);   // -1000: shape not eligible
-    if (rc != -1000) {
-      if (int e = cuda_fail(rc, "decode (plane-streaming kernel) launch")) return e;
-      return launch_epilogues(q, dtype, flags, s);
+    int rc = -1000;
+    if (!(flags & RTM3D_FLAG_LEGACY_PLANES)) {
+      rc = scan_and_select(q, L, reinterpret_cast<unsigned char*>(p.tickets) - L.tickets_off, dtype, flags, s);
+      if (rc > 0 || (rc < 0 && rc != -1000)) return rc;
+    } else {
+      rc = rtm3d::launch_planes(q, dtype, static_cast<int>((flags >> 8) & 0xFu), (flags & RTM3D_FLAG_NO_SPECULATION) ? 0 : 1,
+                                static_cast<int>((flags >> 16) & 0xFFu), static_cast<int>((flags >> 24) & 0xFu), s);   // -1000: shape not eligible
+      if (rc != -1000) if (int e = cuda_fail(rc, "decode (plane-streaming kernel) launch")) return e;
     }
+    if (rc != -1000) return launch_epilogues(q, dtype, flags, s);
   }
   if (L.generic_smem > 200 * 1024) return fail(RTM3D_ERR_SHAPE, "row too wide for the generic kernel (%zu B smem)", L.generic_smem);
   return cuda_fail(rtm3d::launch_generic(p, dtype, mode, L.generic_smem, s), "decode (generic kernel) launch");
@@ -122,10 +157,13 @@ const char* rtm3d_build_info(void) {
       " group_vertices, box3d; fp32+bf16 inputs";
 }
 
-/* developer instrumentation (tools/plane_stats.py); deliberately absent from include/rtm3d_decode.h */
+#ifdef RTM3D_DEV
+/* developer instrumentation (tools/scan_stats.py, tools/plane_stats.py): only in `make DEV=1` builds, never in the
+   production library, and deliberately absent from include/rtm3d_decode.h */
 void rtm3d_debug_set_copy_rows(int rows) { rtm3d::debug_set_copy_rows(rows); }
 void rtm3d_debug_set_trace(void* t) { rtm3d::debug_set_trace(static_cast<unsigned long long*>(t)); }
 void rtm3d_debug_set_stats(void* dev_u64_16) { rtm3d::debug_set_stats(static_cast<unsigned long long*>(dev_u64_16)); }
+#endif
 
 int rtm3d_decode_workspace_bytes(int B, int C, int H, int W, int K, size_t* out_bytes) {
   if (!out_bytes) return fail(RTM3D_ERR_NULL, "out_bytes is NULL");
@@ -287,10 +325,16 @@ int rtm3d_decode_fused(const void* hm, const void* off, const void* off2, const 
     q.retry = reinterpret_cast<uint32_t*>(base + L.retry_off);
     q.guess = reinterpret_cast<uint32_t*>(base + L.guess_off);
     q.ftable = reinterpret_cast<const float*>(base + L.table_off);
-    const int rc = rtm3d::launch_planes(q, dtype, static_cast<int>((flags >> 8) & 0xFu), (flags & RTM3D_FLAG_NO_SPECULATION) ? 0 : 1,
-                                        static_cast<int>((flags >> 16) & 0xFFu), static_cast<int>((flags >> 24) & 0xFu), s);
+    int rc = -1000;
+    if (!(flags & RTM3D_FLAG_LEGACY_PLANES)) {
+      rc = scan_and_select(q, L, ws, dtype, flags, s);
+      if (rc > 0 || (rc < 0 && rc != -1000)) return rc;
+    } else {
+      rc = rtm3d::launch_planes(q, dtype, static_cast<int>((flags >> 8) & 0xFu), (flags & RTM3D_FLAG_NO_SPECULATION) ? 0 : 1,
+                                static_cast<int>((flags >> 16) & 0xFFu), static_cast<int>((flags >> 24) & 0xFu), s);
+      if (rc != -1000) if (int e = cuda_fail(rc, "decode (plane-streaming kernel, fused) launch")) return e;
+    }
     if (rc != -1000) {
-      if (int e = cuda_fail(rc, "decode (plane-streaming kernel, fused) launch")) return e;
       fused = true;
       // everything after the selection in one kernel, unless the caller wants the stages separately (bench.py's marks)
       if (!(flags & (RTM3D_FLAG_NO_EPILOGUE | RTM3D_FLAG_NO_GROUP)) &&

@@ -34,6 +34,11 @@ __device__ __forceinline__ uint64_t make_key(float score, uint32_t flat) {
 __device__ __forceinline__ float key_score(uint64_t k) { return __uint_as_float(static_cast<uint32_t>(k >> 32)); }
 __device__ __forceinline__ uint32_t key_flat(uint64_t k) { return 0xFFFFFFFFu - static_cast<uint32_t>(k); }
 
+// order-preserving map float -> u32 and back (NaN patterns land beyond +-inf and never compare as candidates)
+__host__ __device__ __forceinline__ uint32_t f32_ord_bits(uint32_t b) { return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+__device__ __forceinline__ uint32_t f32_ord(float f) { return f32_ord_bits(__float_as_uint(f)); }
+__device__ __forceinline__ float f32_unord(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u); }
+
 // ---- conservative logit-domain filters --------------------------------------------------------------------------
 // The scan compares LOGITS and evaluates the exact sigmoid only for the few pixels that survive.  All margins below
 // are chosen so that, with the computed sigmoid within a few ulp of the real one, a pixel rejected in the logit

@@ -161,6 +161,20 @@ WorkspaceLayout workspace_layout(int B, int C, int H, int W, int K) {
   off += 256;
   L.flat_off = off;                                  // [B][K] flat peak indices when the caller does not ask for them
   off += static_cast<size_t>(B) * K * 4;
+  off = (off + 255) / 256 * 256;
+  L.queue_off = off;                                 // strip counter of the scan kernel
+  off += 256;
+  // candidate lists of the scan kernel: one per strip.  Room for the strips the kernel chooses by itself (either element
+  // type) and, while that stays small, for the 8 strips per plane a caller may force.
+  L.cand_cap = scan_list_cap(K);
+  int sp = scan_max_strips_per_plane(H, W, K);
+  if (sp < 8 && static_cast<size_t>(B) * C * 8 * L.cand_cap * 8 <= (32u << 20)) sp = 8;
+  if (sp < 2) sp = 2;
+  L.cand_strips = B * C * sp;
+  L.cand_count_off = off;
+  off += (static_cast<size_t>(L.cand_strips) * 4 + 255) / 256 * 256;
+  L.cand_off = off;
+  off += static_cast<size_t>(L.cand_strips) * L.cand_cap * 8;
   L.total = (off + 255) / 256 * 256;
   return L;
 }

@@ -1154,7 +1154,8 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) decode_planes_kernel(const P
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-static int g_sm_count = 0;
+#ifdef RTM3D_DEV
+// developer instrumentation: process-global knobs, compiled only into `make DEV=1` builds
 static unsigned long long* g_stats = nullptr;
 static int g_stages_override = 0;
 static unsigned long long* g_trace = nullptr;
@@ -1162,6 +1163,24 @@ void debug_set_trace(unsigned long long* t) { g_trace = t; }
 static int g_copy_rows = 0;   // developer knob (debug_set_copy_rows): rows per bulk copy, 0 = whole chunk
 void debug_set_copy_rows(int r) { if (r >= 1000) { g_stages_override = r - 1000; g_copy_rows = 0; } else g_copy_rows = r; }
 void debug_set_stats(unsigned long long* dev_u64_16) { g_stats = dev_u64_16; }
+unsigned long long* debug_get_stats() { return g_stats; }
+#else
+static unsigned long long* const g_stats = nullptr;
+static unsigned long long* const g_trace = nullptr;
+constexpr int g_stages_override = 0;
+constexpr int g_copy_rows = 0;
+#endif
+// multiprocessor count of the current device (a process may drive several GPUs)
+static int plane_sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (dev >= 0 && dev < 64 && cached[dev] > 0) return cached[dev];
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { cudaGetLastError(); return 0; }
+  if (dev >= 0 && dev < 64) cached[dev] = n;
+  return n;
+}
 
 static bool make_plane_geom(const PlaneParams& p, int dtype, int split_override, int speculate, PlaneGeom& g) {
   const int es = dtype == 0 ? 4 : 2;
@@ -1170,14 +1189,8 @@ static bool make_plane_geom(const PlaneParams& p, int dtype, int split_override,
   if ((p.hm_main && reinterpret_cast<uintptr_t>(p.hm_main) % 16 != 0) || (p.hm_kpt && reinterpret_cast<uintptr_t>(p.hm_kpt) % 16 != 0)) return false;
   const int row_bytes = p.W * es;
   if (row_bytes > 8192) return false;
-  if (g_sm_count == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
-      cudaGetLastError();
-      return false;
-    }
-    g_sm_count = n;
-  }
+  const int g_sm_count = plane_sm_count();
+  if (g_sm_count <= 0) return false;
   const long long planes = static_cast<long long>(p.B) * ((p.C > 0 ? 1 : 0) + p.Cv);   // items per strip index (the C main planes are one item)
   // Strips per plane.  Splitting a selection problem over several CTAs costs a publish + merge through global memory on
   // the finisher warps, which are the busiest part of a CTA: measured, split = 1 is never slower for batches of 1..256
@@ -1260,6 +1273,7 @@ static int launch_planes_t(const PlaneParams& p, const PlaneGeom& g, cudaStream_
   auto kern = decode_planes_kernel<T, STATS, DBG, SPLIT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.smem));
   if (e != cudaSuccess) return static_cast<int>(e);
+  const int g_sm_count = plane_sm_count();
   int grid = g.n_items < g_sm_count ? g.n_items : g_sm_count;
   if (g.max_ctas > 0 && grid > g.max_ctas) grid = g.max_ctas;
   kern<<<grid, kPlaneThreads, g.smem, s>>>(p, g);

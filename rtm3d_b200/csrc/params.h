@@ -54,8 +54,37 @@ struct PlaneParams {
   unsigned long long* stats;  // developer counters (nullable; decode_planes.cu StatSlot)
 };
 
+// cand_count word of a strip: low 31 bits = keys in the list; top bit set = the keys are (score, index) keys (exact path),
+// clear = (ordered logit, index) keys whose sigmoid the select kernel evaluates
+constexpr uint32_t kCandScoreKeys = 0x80000000u;
+
+// Parameters of the plane-resident scan kernel (scan_planes.cu).  Either heat-map may be absent (C or Cv = 0).
+struct ScanParams {
+  const void* hm_main;   // [B,C,H,W]  main_kf logits            (nullptr when C == 0)
+  const void* hm_kpt;    // [B,Cv,H,W] keypoint heat-map logits  (nullptr when Cv == 0)
+  int B, C, Cv, H, W, K;
+  float thresh;
+  float t0;              // logit-domain prefilter derived from thresh (x < t0 => sigmoid(x) <= thresh)
+  unsigned long long* cand;   // [strips][list_cap] candidate keys per strip (unordered)
+  uint32_t* cand_count;       // [strips]
+  uint32_t* queue;            // [1] strip counter, 0 between launches (wraps back to 0 by itself)
+  uint32_t* status;           // watchdog word (0 = ok)
+  unsigned long long* stats;  // developer counters (nullable)
+};
+
+// Selection after the scan (select.cu): merge the strip lists of every selection problem, exact top-K, sort, write
+// score / flat / counts (Tier A) and kscore / kflat (Tier B, with the 0.0-score fillers).
+struct SelectParams {
+  const unsigned long long* cand; const uint32_t* cand_count;
+  int B, C, Cv, H, W, K, Sp, list_cap;
+  float thresh;
+  float* score; int32_t* flat; int32_t* counts;      // Tier A (C > 0)
+  float* kscore; int32_t* kflat;                      // Tier B (Cv > 0)
+};
+
 struct WorkspaceLayout {
-  size_t table_off, tickets_off, status_off, keys_off, counts_off, retry_off, guess_off, flat_off, total;
+  size_t table_off, tickets_off, status_off, keys_off, counts_off, retry_off, guess_off, flat_off, queue_off, cand_off, cand_count_off, total;
+  int cand_strips, cand_cap;     // capacity of the scan kernel's candidate lists
   int strip_rows, nstrips, list_cap;
   size_t generic_smem;
 };
@@ -69,12 +98,22 @@ int launch_generic(const DecodeParams& p, int dtype, int mode, size_t smem, cuda
 // path).  split_override: strips per plane (0 = choose).
 int launch_planes(const PlaneParams& p, int dtype, int split_override, int speculate, int max_ctas, int debug, cudaStream_t s);
 bool planes_eligible(const PlaneParams& p, int dtype);
+// plane-resident scan kernel + selection (scan_planes.cu, select.cu); launch_scan returns -1000 when the shape is not eligible
+int launch_scan(const ScanParams& p, int dtype, int strips_override, int max_ctas, int debug, cudaStream_t s, int* strips_per_plane,
+                int* list_cap);
+bool scan_eligible(int B, int C, int Cv, int H, int W, int K, int dtype, const void* hm_main, const void* hm_kpt);
+int scan_max_strips_per_plane(int H, int W, int K);
+int scan_strips_per_plane(int H, int W, int K, int dtype, int strips_override);   // 0 = not eligible
+int scan_list_cap(int K);
+size_t select_smem_bytes(int C, int Cv, int Sp, int list_cap, int K);
+int launch_select(const SelectParams& p, cudaStream_t s);
 constexpr int kPlanesMaxSplit = 8;
 constexpr int kFilterTableWords = 2048;        // >= histogram bins + 1; the last word holds kFilterTableMagic
 constexpr unsigned kFilterTableMagic = 0x5A17AB1Eu;
 int launch_filter_table(float* table, cudaStream_t s);   // fills a workspace's table (rtm3d_workspace_init)
 int threshold_table_bins();
 void debug_set_stats(unsigned long long* dev_u64_16);
+unsigned long long* debug_get_stats();
 void debug_set_trace(unsigned long long* dev_u64_960);
 void debug_set_copy_rows(int rows);   // developer instrumentation, not part of the public ABI
 int launch_threshold_table(float* t, uint32_t* edge, cudaStream_t s);

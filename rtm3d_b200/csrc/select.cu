@@ -1,0 +1,121 @@
+// Selection after the scan kernel (general path, any K <= 1024 and any number of strips per plane): one CTA per selection
+// problem -- the C planes of an image (flat top-K over C*H*W, models/model.py:87-98) or one keypoint plane (per-channel
+// top-K, models/model.py:109-114).  The CTA merges the candidate lists of the problem's strips (each provably contains its
+// strip's K best peaks, scan_planes.cu), selects the exact K best keys, sorts them by (score desc, index asc) and writes
+// score / flat / counts (Tier A) or kscore / kflat with the 0.0-score fillers (Tier B).
+#include "common.cuh"
+#include "params.h"
+
+namespace rtm3d {
+
+constexpr int kSelThreads = 256;
+
+// Tier B rows cnt..K-1: the lowest flat indices that are not among the plane's positive-score peaks (what a top-K over the
+// zero-filled peak map returns).  One warp; scratch >= 3K+8 words.
+static __device__ __noinline__ void warp_fill_kpt(const SelectParams& p, size_t row0, const uint64_t* sorted, int cnt,
+                                                  uint32_t* scratch, int lane) {
+  const int K = p.K, HW = p.H * p.W;
+  uint32_t* fill = scratch + 2 * K;             // [K] filler indices (rows cnt..K-1)
+  if (cnt < K) {
+    const int span = min(K + cnt, HW);          // the first K-cnt non-candidate indices lie in [0, K+cnt)
+    uint32_t* taken = scratch;                  // [span]
+#pragma unroll 1
+    for (int i = lane; i < span; i += 32) {
+      uint32_t t = 0;
+#pragma unroll 1
+      for (int q = 0; q < cnt; ++q) t |= (key_flat(sorted[q]) == static_cast<uint32_t>(i));
+      taken[i] = t;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      int r = cnt;
+#pragma unroll 1
+      for (int i = 0; i < span && r < K; ++i)
+        if (!taken[i]) fill[r++] = i;
+    }
+    __syncwarp();
+  }
+#pragma unroll 1
+  for (int j = lane; j < K; j += 32) {
+    p.kscore[row0 + j] = j < cnt ? key_score(sorted[j]) : 0.0f;
+    p.kflat[row0 + j] = static_cast<int32_t>(j < cnt ? key_flat(sorted[j]) : fill[j]);
+  }
+}
+
+__global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p, int n_max) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int K = p.K, kpad = next_pow2(K), tid = threadIdx.x;
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);                  // [n_max]
+  uint64_t* best = keys + n_max;                                           // [kpad]
+  uint32_t* hist = reinterpret_cast<uint32_t*>(best + kpad);               // [264]
+  uint32_t* scratch = hist + 264;                                          // [3K+8]
+  const int n_main = p.C > 0 ? p.B : 0;
+  const int q = blockIdx.x;
+  const bool is_main = q < n_main;
+  const int first = is_main ? q * p.C * p.Sp : (p.B * p.C + (q - n_main)) * p.Sp;
+  const int n_lists = is_main ? p.C * p.Sp : p.Sp;
+  // gather the lists; (logit, index) keys become (score, index) keys here, pixels at or below the score floor drop out
+  // (strict `score > thresh` of models/model.py:91; 0.0 for the keypoint planes: zero-score pixels are fillers, not peaks)
+  __shared__ uint32_t s_n;
+  if (tid == 0) s_n = 0u;
+  __syncthreads();
+  const float lim = is_main ? p.thresh : 0.0f;
+  for (int l = 0; l < n_lists; ++l) {
+    const uint32_t raw = p.cand_count[first + l];
+    const int cnt = static_cast<int>(raw & ~kCandScoreKeys);
+    const bool score_keys = (raw & kCandScoreKeys) != 0u;
+    const unsigned long long* src = p.cand + static_cast<size_t>(first + l) * p.list_cap;
+    for (int i = tid; i < cnt; i += kSelThreads) {
+      unsigned long long k = src[i];
+      bool valid = true;
+      if (!score_keys) {
+        const float sc = sigmoid_ref(f32_unord(static_cast<uint32_t>(k >> 32)));
+        valid = sc > lim;
+        k = make_key(sc, key_flat(k));
+      }
+      if (valid) keys[atomicAdd(&s_n, 1u)] = k;
+    }
+  }
+  __syncthreads();
+  const int n = static_cast<int>(s_n);
+  const int have = block_select_topk(keys, n, K, best, hist);
+  for (int i = have + tid; i < kpad; i += kSelThreads) best[i] = 0ull;
+  __syncthreads();
+  block_bitonic_sort_desc(best, kpad);
+  if (is_main) {
+    // every key of a main list has score > thresh already (models/model.py:91): counts = number of keys
+    const int b = q;
+    for (int j = tid; j < K; j += kSelThreads) {
+      const size_t row = static_cast<size_t>(b) * K + j;
+      const bool valid = j < have;
+      p.score[row] = valid ? key_score(best[j]) : 0.f;
+      p.flat[row] = valid ? static_cast<int32_t>(key_flat(best[j])) : -1;
+    }
+    if (tid == 0) p.counts[b] = have;
+  } else if (tid < 32) {
+    warp_fill_kpt(p, static_cast<size_t>(q - n_main) * K, best, have, scratch, tid);
+  }
+}
+
+size_t select_smem_bytes(int C, int Cv, int Sp, int list_cap, int K) {
+  const int lists = (C > 0 ? C : 1) * Sp;
+  return static_cast<size_t>(lists) * list_cap * 8 + static_cast<size_t>(next_pow2(K)) * 8 + 264 * 4 + (3 * static_cast<size_t>(K) + 8) * 4;
+}
+
+int launch_select(const SelectParams& p, cudaStream_t s) {
+  const size_t smem = select_smem_bytes(p.C, p.Cv, p.Sp, p.list_cap, p.K);
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  const int n_max = (p.C > 0 ? p.C : 1) * p.Sp * p.list_cap;
+  const unsigned grid = static_cast<unsigned>((p.C > 0 ? p.B : 0) + p.B * p.Cv);
+  select_kernel<<<grid, kSelThreads, smem, s>>>(p, n_max);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace rtm3d

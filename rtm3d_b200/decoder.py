@@ -111,7 +111,8 @@ class HeatmapDecoder:
     (DETECTOR.SCORE_THRESH, DETECTOR.TOPK_CANDIDATES, MODEL.DOWN_SAMPLE -- models/model.py:41-42,67,70)."""
 
     def __init__(self, score_thresh: float = 0.5, topk: int = 30, down_sample: float = 4.0, force_generic: bool = False,
-                 split: int = 0, speculate: bool = True, max_ctas: int = 0, reuse_outputs: bool = False):
+                 split: int = 0, speculate: bool = True, max_ctas: int = 0, reuse_outputs: bool = False, legacy: bool = False,
+                 debug: int = 0):
         if not (score_thresh >= 0):
             raise ValueError("score_thresh must be >= 0: zero-score fillers of the peak map could pass a negative threshold")
         if not (1 <= int(topk) <= 1024):
@@ -120,11 +121,14 @@ class HeatmapDecoder:
         self.topk = int(topk)
         self.down_sample = float(down_sample)
         if split not in (0, 1, 2, 4, 8):
-            raise ValueError("split (strips per plane of the plane-streaming kernel) must be 0 (auto), 1, 2, 4 or 8")
+            raise ValueError("split (strips per plane of the streaming kernels) must be 0 (auto), 1, 2, 4 or 8")
         if not (0 <= int(max_ctas) <= 255):
             raise ValueError("max_ctas must be in [0, 255] (0 = one CTA per SM)")
+        # legacy: the round-1 plane-streaming kernel instead of the plane-resident scan kernel (speculate only applies to it);
+        # debug (tests): 1 = the scan kernel's first threshold is forced too high (deepening path), 2 = tiny candidate lists
+        # (exact radix path), 3 = both
         self.flags = ((_native.FLAG_FORCE_GENERIC if force_generic else 0) | (0 if speculate else _native.FLAG_NO_SPECULATION)
-                      | (split << 8) | (int(max_ctas) << 16))
+                      | (_native.FLAG_LEGACY_PLANES if legacy else 0) | (split << 8) | (int(max_ctas) << 16) | ((int(debug) & 0xF) << 24))
         self._lib = _native.lib()
         self._ws = {}
         # reuse_outputs: decode_packed / decode_with_keypoints return the SAME result buffers on every call with the same

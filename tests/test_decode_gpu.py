@@ -19,8 +19,10 @@ DEV = "cuda:0"
 FLOAT_FIELDS = ("score", "proj", "verts", "bbox")
 # kernel variants: the shape-generic strip kernels, the plane-streaming kernel with its own choice of strips per plane
 # (falls back to generic on ineligible shapes), and the plane-streaming kernel forced to 1/2/4/8 strips per plane
-VARIANTS = [dict(force_generic=True), dict(), dict(split=1), dict(split=2), dict(split=4), dict(split=8)]
-VARIANT_IDS = ["generic", "auto", "s1", "s2", "s4", "s8"]
+# (the scan kernel with 1/2/4/8 strips per plane, its deepening and exact-radix paths forced, and the round-1 kernel)
+VARIANTS = [dict(force_generic=True), dict(), dict(split=1), dict(split=2), dict(split=4), dict(split=8),
+            dict(debug=1), dict(debug=2), dict(debug=3, split=2), dict(legacy=True), dict(legacy=True, split=2)]
+VARIANT_IDS = ["generic", "auto", "s1", "s2", "s4", "s8", "deepen", "exact", "deepen-exact-s2", "legacy", "legacy-s2"]
 
 
 def _rows(packed, b):
@@ -193,11 +195,13 @@ def test_repeatable_and_workspace_self_cleaning():
 
 
 @pytest.mark.parametrize("max_ctas", [1, 3, 0])
-@pytest.mark.parametrize("speculate", [True, False])
-def test_speculative_start_threshold_is_exact(max_ctas, speculate):
-    """The plane-streaming kernel starts a plane at the threshold remembered from the previous plane of the same index
-    (a few bins lower) and redoes the plane when that turns out too high.  Batches whose images alternate between
-    strong, weak, empty and plateau maps make the guess fail constantly; few CTAs make every CTA see many planes."""
+@pytest.mark.parametrize("kernel", [dict(), dict(debug=1), dict(legacy=True), dict(legacy=True, speculate=False)],
+                         ids=["scan", "scan-deepen", "legacy", "legacy-nospec"])
+def test_thresholds_chosen_by_the_kernels_never_leak_into_the_result(max_ctas, kernel):
+    """The scan kernel picks a threshold per strip from an order statistic of the strip's own maxima and verifies it; the
+    round-1 kernel starts a plane at the threshold remembered from the previous plane of the same index and redoes the
+    plane when that turns out too high.  Batches whose images alternate between strong, weak, empty and plateau maps make
+    any guess fail constantly; few CTAs make every CTA see many planes."""
     B, C, H, W, K = 24, 3, 48, 80, 50
     logits, kpt = synth.head_outputs(B, C, H, W, seed=4242, kind="randn", kpt_channels=9)
     scale = torch.tensor([3.0, 0.05, 1.0, 0.3, 6.0, 0.0])[torch.arange(B) % 6].view(B, 1, 1, 1)
@@ -205,7 +209,7 @@ def test_speculative_start_threshold_is_exact(max_ctas, speculate):
     logits[0] = logits[0] * scale + shift
     kpt = kpt * scale + shift
     dev_logits = [t.to(DEV) for t in logits]
-    dec = HeatmapDecoder(0.4, K, 4.0, speculate=speculate, max_ctas=max_ctas)
+    dec = HeatmapDecoder(0.4, K, 4.0, max_ctas=max_ctas, **kernel)
     packed = dec.decode_packed(dev_logits)
     cand = dec.decode_keypoints(kpt.to(DEV), dev_logits[3])
     torch.cuda.synchronize()

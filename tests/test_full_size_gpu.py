@@ -76,8 +76,9 @@ def test_full_size_properties_and_spot_checks(shape):
     fb, fg = ("score", "xy", "flat"), ("kpt_proj", "kpt_score", "kpt_j", "verts")
     det2, cand2, grp2 = dec.decode_with_keypoints(logits, kpt)
     _same(det, det2, fa); _same(cand, cand2, fb); _same(grp, grp2, fg)
-    det3, cand3, grp3 = HeatmapDecoder(0.4, K, 4.0, speculate=False).decode_with_keypoints(logits, kpt)
-    _same(det, det3, fa); _same(cand, cand3, fb); _same(grp, grp3, fg)
+    for other in (dict(legacy=True), dict(legacy=True, speculate=False), dict(debug=1)):   # round-1 kernel; scan kernel forced to deepen
+        det3, cand3, grp3 = HeatmapDecoder(0.4, K, 4.0, **other).decode_with_keypoints(logits, kpt)
+        _same(det, det3, fa); _same(cand, cand3, fb); _same(grp, grp3, fg)
     det4, cand4, grp4 = HeatmapDecoder(0.4, K, 4.0).decode_with_keypoints(logits, kpt, fused=False)
     _same(det, det4, fa); _same(cand, cand4, fb); _same(grp, grp4, fg)
     # fewer CTAs than SMs (bench.py at N > 1 leaves four SMs to NCCL), strips (the publish + merge path), reused result buffers

@@ -13,8 +13,9 @@ from rtm3d_b200 import HeatmapDecoder, synth
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 # fused: both heat-maps in one launch of the plane-streaming kernel (rtm3d_decode_fused); separate: the three entry points
-VARIANTS = [dict(force_generic=True), dict(), dict(split=1), dict(split=2), dict(split=4), dict(fused=False), dict(fused=False, split=2)]
-VARIANT_IDS = ["generic", "auto", "s1", "s2", "s4", "separate", "separate-s2"]
+VARIANTS = [dict(force_generic=True), dict(), dict(split=1), dict(split=2), dict(split=4), dict(fused=False), dict(fused=False, split=2),
+            dict(debug=1), dict(debug=2), dict(debug=3, split=2), dict(legacy=True), dict(legacy=True, split=2)]
+VARIANT_IDS = ["generic", "auto", "s1", "s2", "s4", "separate", "separate-s2", "deepen", "exact", "deepen-exact-s2", "legacy", "legacy-s2"]
 
 
 def _check(logits_cpu, kpt_cpu, K, variant, what):
