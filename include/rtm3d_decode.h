@@ -53,6 +53,8 @@ enum rtm3d_error {
                                    caller runs rtm3d_epilogue_main / rtm3d_epilogue_keypoints itself */
 #define RTM3D_FLAG_LEGACY_PLANES 16u /* use the round-1 plane-streaming kernel (histogram select inside the streaming CTA) instead of
                                        the plane-resident scan kernel + select kernel */
+#define RTM3D_FLAG_NO_SELECT 32u /* rtm3d_decode_fused: stop after the scan kernel (candidate lists in the workspace); the caller
+                                   continues with rtm3d_select_post on the same workspace */
 #define RTM3D_FLAG_MAX_CTAS(n) (((unsigned)(n) & 0xFFu) << 16) /* plane-streaming kernel: at most n CTAs (0 = one per SM) */
 #define RTM3D_FLAG_SPLIT(s) (((unsigned)(s) & 0xFu) << 8) /* plane-streaming kernel: force s strips (1,2,4,8) per plane; 0 = auto */
 /* bits 24..27: developer timing experiments of the plane-streaming kernel (tools/debug_time.py; results are then WRONG);
@@ -186,6 +188,20 @@ int rtm3d_post_fused(const int32_t* flat, const int32_t* counts, const int32_t* 
                      int B, int C, int Cv, int H, int W, int n_vert, int K, float down,
                      int64_t* cls, float* proj, float* verts, float* bbox, float* kxy,
                      float* kpt_proj, float* kpt_score, int32_t* kpt_j, float* verts_cv, void* stream);
+
+/*
+ * Second half of rtm3d_decode_fused when it was called with RTM3D_FLAG_NO_SELECT (it then stops after the scan kernel, whose
+ * per-strip candidate lists stay in the workspace): merges and sorts the lists of every selection problem -- the flat top-K
+ * over C*H*W of models/model.py:87-98 and the per-channel top-K of :109-114 -- and runs everything rtm3d_post_fused does, in
+ * ONE kernel (a cluster of four CTAs per image).  Same arguments (and the same `flags`: the strips-per-plane override must
+ * match) as the rtm3d_decode_fused call that filled `ws`; the selection outputs score / flat / counts / kscore / kflat are
+ * written here.  rtm3d_decode_fused enqueues this kernel itself unless a flag asks for the stages separately.
+ */
+int rtm3d_select_post(const void* off, const void* off2, const void* voff2, int dtype,
+                      int B, int C, int Cv, int H, int W, int n_vert, int K, float thresh, float down,
+                      int64_t* cls, float* score, float* proj, float* verts, float* bbox, int32_t* flat, int32_t* counts,
+                      float* kscore, float* kxy, int32_t* kflat, float* kpt_proj, float* kpt_score, int32_t* kpt_j,
+                      float* verts_cv, void* ws, size_t ws_bytes, unsigned flags, void* stream);
 
 /*
  * Tier B -- _group_vertexs_kf (models/model.py:134-162): for every detection n of rtm3d_decode_main and keypoint

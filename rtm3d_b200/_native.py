@@ -18,6 +18,7 @@ FLAG_NO_SPECULATION = 2
 FLAG_NO_GROUP = 4
 FLAG_NO_EPILOGUE = 8
 FLAG_LEGACY_PLANES = 16
+FLAG_NO_SELECT = 32
 
 _c = ctypes
 _vp, _i, _f, _sz, _u = _c.c_void_p, _c.c_int, _c.c_float, _c.c_size_t, _c.c_uint
@@ -43,6 +44,8 @@ SIGNATURES = {
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _u, _vp],
     "rtm3d_post_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f,
                          _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "rtm3d_select_post": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f,
+                          _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _u, _vp],
     "rtm3d_group_vertices": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp],
     "rtm3d_pack_wire": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],
     "rtm3d_sigmoid_f32": [_vp, _vp, _sz, _vp],

@@ -77,7 +77,9 @@ int launch_epilogues(const rtm3d::PlaneParams& q, int dtype, unsigned flags, cud
 
 // Plane-resident scan kernel + selection: writes score / flat / counts (C > 0) and kscore / kflat (Cv > 0).
 // Returns -1000 when the shape is not eligible for the scan kernel (the caller falls back).
-int scan_and_select(const rtm3d::PlaneParams& q, const rtm3d::WorkspaceLayout& L, void* ws, int dtype, unsigned flags, cudaStream_t s) {
+// post: when given (rtm3d_decode_fused), the selection and everything after it run in ONE kernel behind the scan kernel.
+int scan_and_select(const rtm3d::PlaneParams& q, const rtm3d::WorkspaceLayout& L, void* ws, int dtype, unsigned flags, cudaStream_t s,
+                    const rtm3d::PostFusedParams* post = nullptr) {
   unsigned char* base = static_cast<unsigned char*>(ws);
   rtm3d::ScanParams sp{};
   sp.hm_main = q.hm_main; sp.hm_kpt = q.hm_kpt;
@@ -101,6 +103,11 @@ int scan_and_select(const rtm3d::PlaneParams& q, const rtm3d::WorkspaceLayout& L
   const int rc = rtm3d::launch_scan(sp, dtype, strips_override, static_cast<int>((flags >> 16) & 0xFFu), static_cast<int>((flags >> 24) & 0xFu), s, &Sp, &cap);
   if (rc == -1000) return rc;
   if (int e = cuda_fail(rc, "decode (scan kernel) launch")) return e;
+  if (flags & RTM3D_FLAG_NO_SELECT) return 0;                       // the caller continues with rtm3d_select_post (bench.py's marks)
+  if (post) {
+    rtm3d::SelectPostParams f{sp.cand, sp.cand_count, Sp, cap, q.thresh, q.score, q.flat, q.counts, q.kscore, q.kflat, *post};
+    return cuda_fail(rtm3d::launch_select_post(f, dtype, s), "decode (select + post kernel) launch");
+  }
   rtm3d::SelectParams sel{sp.cand, sp.cand_count, q.B, q.C, q.Cv, q.H, q.W, q.K, Sp, cap, q.thresh, q.score, q.flat, q.counts, q.kscore, q.kflat};
   return cuda_fail(rtm3d::launch_select(sel, s), "decode (select kernel) launch");
 }
@@ -327,8 +334,13 @@ int rtm3d_decode_fused(const void* hm, const void* off, const void* off2, const 
     q.ftable = reinterpret_cast<const float*>(base + L.table_off);
     int rc = -1000;
     if (!(flags & RTM3D_FLAG_LEGACY_PLANES)) {
-      rc = scan_and_select(q, L, ws, dtype, flags, s);
+      // scan kernel, then selection + epilogues + grouping in one kernel -- unless the caller wants the stages separately
+      const bool one_kernel = !(flags & (RTM3D_FLAG_NO_EPILOGUE | RTM3D_FLAG_NO_GROUP)) && rtm3d::select_post_smem(Cv, K, n_vert) <= 200 * 1024;
+      rtm3d::PostFusedParams f{flat, counts, kflat, kscore, off, off2, voff2, B, C, Cv, H, W, n_vert, K, down,
+                               cls, proj, verts, bbox, kxy, kpt_proj, kpt_score, kpt_j, verts_cv};
+      rc = scan_and_select(q, L, ws, dtype, flags, s, one_kernel ? &f : nullptr);
       if (rc > 0 || (rc < 0 && rc != -1000)) return rc;
+      if (rc == 0 && (one_kernel || (flags & RTM3D_FLAG_NO_SELECT))) return 0;
     } else {
       rc = rtm3d::launch_planes(q, dtype, static_cast<int>((flags >> 8) & 0xFu), (flags & RTM3D_FLAG_NO_SPECULATION) ? 0 : 1,
                                 static_cast<int>((flags >> 16) & 0xFFu), static_cast<int>((flags >> 24) & 0xFu), s);
@@ -412,6 +424,31 @@ int rtm3d_decode_fused_host(const void* hm_host, const void* off_host, const voi
   return rtm3d_decode_fused(dev_hm, d_off, d_off2, dev_kpt, d_voff2, dtype, B, C, Cv, H, W, n_vert, K, thresh, down, cls, score, proj,
                             verts, bbox, flat, counts, kscore, kxy, kflat, kpt_proj, kpt_score, kpt_j, verts_cv, ws, ws_bytes, flags,
                             stream);
+}
+
+int rtm3d_select_post(const void* off, const void* off2, const void* voff2, int dtype, int B, int C, int Cv, int H, int W, int n_vert,
+                      int K, float thresh, float down, int64_t* cls, float* score, float* proj, float* verts, float* bbox,
+                      int32_t* flat, int32_t* counts, float* kscore, float* kxy, int32_t* kflat, float* kpt_proj, float* kpt_score,
+                      int32_t* kpt_j, float* verts_cv, void* ws, size_t ws_bytes, unsigned flags, void* stream) {
+  if (!off || !off2 || !voff2 || !cls || !score || !proj || !verts || !bbox || !flat || !counts || !kscore || !kxy || !kflat ||
+      !kpt_proj || !kpt_score || !kpt_j || !ws)
+    return fail(RTM3D_ERR_NULL, "NULL pointer argument");
+  if (dtype != RTM3D_F32 && dtype != RTM3D_BF16) return fail(RTM3D_ERR_DTYPE, "dtype %d", dtype);
+  if (Cv < 1) return fail(RTM3D_ERR_SHAPE, "Cv=%d", Cv);
+  if (int e = check_shape(B, C + Cv, H, W, K)) return e;
+  if (n_vert < 1 || n_vert > RTM3D_MAX_VERTS) return fail(RTM3D_ERR_SHAPE, "n_vert=%d outside [1,%d]", n_vert, RTM3D_MAX_VERTS);
+  if (!(thresh >= 0.0f)) return fail(RTM3D_ERR_THRESH, "score threshold must be >= 0 (got %g)", thresh);
+  const rtm3d::WorkspaceLayout L = rtm3d::workspace_layout(B, C + Cv, H, W, K);
+  if (ws_bytes < L.total) return fail(RTM3D_ERR_WORKSPACE, "workspace %zu B < required %zu B", ws_bytes, L.total);
+  const int Sp = rtm3d::scan_strips_per_plane(H, W, K, dtype, static_cast<int>((flags >> 8) & 0xFu));
+  if (Sp <= 0 || static_cast<long long>(B) * (C + Cv) * Sp > L.cand_strips || rtm3d::select_post_smem(Cv, K, n_vert) > 200 * 1024)
+    return fail(RTM3D_ERR_SHAPE, "shape not served by the scan kernel: no candidate lists in the workspace");
+  unsigned char* base = static_cast<unsigned char*>(ws);
+  rtm3d::PostFusedParams f{flat, counts, kflat, kscore, off, off2, voff2, B, C, Cv, H, W, n_vert, K, down,
+                           cls, proj, verts, bbox, kxy, kpt_proj, kpt_score, kpt_j, verts_cv};
+  rtm3d::SelectPostParams q{reinterpret_cast<const unsigned long long*>(base + L.cand_off), reinterpret_cast<const uint32_t*>(base + L.cand_count_off),
+                            Sp, rtm3d::scan_list_cap(K), thresh, score, flat, counts, kscore, kflat, f};
+  return cuda_fail(rtm3d::launch_select_post(q, dtype, static_cast<cudaStream_t>(stream)), "select + post kernel launch");
 }
 
 int rtm3d_post_fused(const int32_t* flat, const int32_t* counts, const int32_t* kflat, const float* kscore, const void* off,

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "params.h"
 #include "postproc.h"
+#include "select_common.cuh"
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -263,6 +264,249 @@ __global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kPostThread
     p.proj[row * 2 + 1] = valid ? __fmul_rn(p.down, s_m[2 * nl + 1]) : 0.f;
     p.bbox[row * 4 + 0] = lo_x; p.bbox[row * 4 + 1] = lo_y; p.bbox[row * 4 + 2] = hi_x; p.bbox[row * 4 + 3] = hi_y;
   }
+}
+
+// Scattered 4-byte gathers from the regression planes: every scalar is its own 32-byte sector of an NCHW plane.  Without a
+// hint the L2 fetches the whole 128-byte line from DRAM for it (measured: 122 B per gather); .L2::64B halves that.
+template <typename T> __device__ __forceinline__ float gather_ld(const T* p);
+template <> __device__ __forceinline__ float gather_ld<float>(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L2::64B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+template <> __device__ __forceinline__ float gather_ld<__nv_bfloat16>(const __nv_bfloat16* p) {
+  unsigned short u;
+  asm volatile("ld.global.nc.L2::64B.u16 %0, [%1];" : "=h"(u) : "l"(p));
+  return __uint_as_float(static_cast<uint32_t>(u) << 16);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused select + post kernel of rtm3d_decode_fused behind the scan kernel.  A cluster of four CTAs per image:
+//   (S) the image's selection problems are sorted by different CTAs at the same time -- CTA 0: the main problem (its C*Sp
+//       lists), then the centres of the detections (models/model.py:48-50); CTAs 1..3: the keypoint planes (three each for
+//       Cv = 9), each followed by the sub-pixel positions of its K candidates (models/model.py:113-114, :55-57).  Everything
+//       the other CTAs need (candidate positions, detections) is stored into the shared memory of all four.
+//   (2) per (detection, channel): vertex regress (models/model.py:63-69) + nearest candidate (:144-161),
+//   (3) per detection: class, centre, 2D box (:70-73) -- as in post_fused_kernel, same arithmetic and association order.
+struct __align__(8) PostDet { int flat; float mx, my; };
+template <typename T>
+__global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kPostThreads) select_post_kernel(const SelectPostParams sp, int ns) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint32_t s_n;
+  __shared__ int s_count;
+  cg::cluster_group cluster = cg::this_cluster();
+  const PostFusedParams& p = sp.post;
+  const int b = blockIdx.x / kPostSplit, rank = static_cast<int>(cluster.block_rank()), tid = threadIdx.x;
+  const int K = p.K, Cv = p.Cv, V = p.n_vert, HW = p.H * p.W;
+  const int KP = K + 1;                                              // padded row: channels start in different banks
+  const int per = (K + kPostSplit - 1) / kPostSplit;                 // detections per CTA
+  const int n0 = rank * per, n1 = min(K, n0 + per);
+  uint64_t* s_keys = reinterpret_cast<uint64_t*>(smem_raw);           // [ns] sort buffer (tail: filler scratch)
+  float* s_xy = reinterpret_cast<float*>(s_keys + ns);                // [Cv][KP][2] candidate positions
+  float* s_v = s_xy + static_cast<size_t>(Cv) * KP * 2;              // [per*V*2]  scaled regressed vertices (Tier A)
+  PostDet* s_det = reinterpret_cast<PostDet*>(s_v + static_cast<size_t>(per) * V * 2);   // [K] detections: flat index, unscaled centre
+  const T* voff2 = reinterpret_cast<const T*>(p.voff2) + static_cast<size_t>(b) * 2 * HW;
+  const T* off2 = reinterpret_cast<const T*>(p.off2) + static_cast<size_t>(b) * 2 * HW;
+  const T* off = reinterpret_cast<const T*>(p.off) + static_cast<size_t>(b) * 2 * V * HW;
+  float2* peer_xy[kPostSplit];
+  PostDet* peer_det[kPostSplit];
+  int* peer_count[kPostSplit];
+#pragma unroll
+  for (int r = 0; r < kPostSplit; ++r) {
+    peer_xy[r] = reinterpret_cast<float2*>(cluster.map_shared_rank(s_xy, r));
+    peer_det[r] = cluster.map_shared_rank(s_det, r);
+    peer_count[r] = cluster.map_shared_rank(&s_count, r);
+  }
+  cluster.sync();          // every CTA of the cluster has started: its shared memory may be written by its peers from here on
+  // ---- (S) selection problems of this CTA
+  const int n_kpt_ctas = kPostSplit - 1;
+  if (rank == 0) {
+    const int have = block_select_sorted<kPostThreads>(sp.cand, sp.cand_count, sp.list_cap, b * p.C * sp.Sp, p.C * sp.Sp, K, sp.thresh,
+                                                      s_keys, ns, &s_n);
+    // every listed key has score > thresh (models/model.py:91): the image's count is the number of keys
+    for (int j = tid; j < K; j += kPostThreads) {
+      const size_t row = static_cast<size_t>(b) * K + j;
+      const bool valid = j < have;
+      const int fl = valid ? static_cast<int>(key_flat(s_keys[j])) : -1;
+      sp.score[row] = valid ? key_score(s_keys[j]) : 0.f;
+      sp.flat[row] = fl;
+      PostDet dt{fl, 0.f, 0.f};
+      if (valid) {                                                   // centre of the detection (models/model.py:48-50)
+        const int rem = fl % HW;
+        const int yi = rem / p.W, xi = rem - yi * p.W;
+        dt.mx = __fadd_rn(static_cast<float>(xi), sigmoid_ref(gather_ld<T>(off2 + rem)));
+        dt.my = __fadd_rn(static_cast<float>(yi), sigmoid_ref(gather_ld<T>(off2 + HW + rem)));
+      }
+#pragma unroll
+      for (int r = 0; r < kPostSplit; ++r) peer_det[r][j] = dt;
+    }
+    if (tid == 0) {
+      sp.counts[b] = have;
+#pragma unroll
+      for (int r = 0; r < kPostSplit; ++r) *peer_count[r] = have;
+    }
+  } else {
+    for (int kc = rank - 1; kc < Cv; kc += n_kpt_ctas) {
+      const int plane = p.B * p.C + b * Cv + kc;
+      const int have = block_select_sorted<kPostThreads>(sp.cand, sp.cand_count, sp.list_cap, plane * sp.Sp, sp.Sp, K, 0.0f, s_keys, ns, &s_n);
+      const size_t row0 = (static_cast<size_t>(b) * Cv + kc) * K;
+      // rows have..K-1: 0.0-score fillers = the lowest flat indices that are not among the plane's positive-score peaks (what a
+      // top-K over the zero-filled peak map returns); with fewer than K valid keys the list held ALL peaks
+      uint32_t* fill = reinterpret_cast<uint32_t*>(s_keys + next_pow2(K));       // [K] filler indices, then [2K+8] "taken" flags
+      if (have < K) {
+        const int span = min(K + have, HW);            // the first K-have non-candidate indices lie in [0, K+have)
+        uint32_t* taken = fill + K;
+        for (int i = tid; i < span; i += kPostThreads) {
+          uint32_t t = 0;
+          for (int q = 0; q < have; ++q) t |= (key_flat(s_keys[q]) == static_cast<uint32_t>(i));
+          taken[i] = t;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          int r = have;
+          for (int i = 0; i < span && r < K; ++i)
+            if (!taken[i]) fill[r++] = i;
+        }
+        __syncthreads();
+      }
+      // candidates: score, index, sub-pixel position (models/model.py:113-114, :55-57)
+      for (int j = tid; j < K; j += kPostThreads) {
+        const bool real = j < have;
+        const int fl = static_cast<int>(real ? key_flat(s_keys[j]) : fill[j]);
+        sp.kscore[row0 + j] = real ? key_score(s_keys[j]) : 0.0f;
+        sp.kflat[row0 + j] = fl;
+        const int yi = fl / p.W, xi = fl - yi * p.W;
+        const float x = __fadd_rn(static_cast<float>(xi), sigmoid_ref(gather_ld<T>(voff2 + fl)));
+        const float y = __fadd_rn(static_cast<float>(yi), sigmoid_ref(gather_ld<T>(voff2 + HW + fl)));
+#pragma unroll
+        for (int r = 0; r < kPostSplit; ++r) peer_xy[r][kc * KP + j] = make_float2(x, y);
+        p.kxy[(row0 + j) * 2] = x; p.kxy[(row0 + j) * 2 + 1] = y;
+      }
+      __syncthreads();                                                // the sort buffer is reused by the next plane
+    }
+  }
+  cluster.sync();          // every CTA of the image has all candidates and detections (and nobody writes into a peer after this)
+  const int n_det = s_count;
+  // ---- (2) per (detection, channel): vertex regress (models/model.py:63-69) + nearest candidate (:144-161)
+  const int KC = (Cv > V ? Cv : V);                                   // channels that need work per detection
+  for (int w = tid; w < (n1 - n0) * KC; w += kPostThreads) {
+    const int nl = w / KC, k = w - nl * KC, n = n0 + nl;
+    const bool valid = n < n_det;
+    float ox = 0.f, oy = 0.f, mx = 0.f, my = 0.f;
+    if (valid) {
+      const PostDet dt = s_det[n];
+      const int rem = dt.flat % HW;
+      mx = dt.mx; my = dt.my;
+      if (k < V) {
+        ox = gather_ld<T>(off + static_cast<size_t>(2 * k) * HW + rem);
+        oy = gather_ld<T>(off + static_cast<size_t>(2 * k + 1) * HW + rem);
+      }
+    }
+    const float vx = valid ? __fmul_rn(p.down, __fadd_rn(ox, mx)) : 0.f;
+    const float vy = valid ? __fmul_rn(p.down, __fadd_rn(oy, my)) : 0.f;
+    if (k < V) {
+      s_v[(nl * V + k) * 2] = vx; s_v[(nl * V + k) * 2 + 1] = vy;
+      float* vout = p.verts + ((static_cast<size_t>(b) * K + n) * V + k) * 2;
+      vout[0] = vx; vout[1] = vy;
+    }
+    if (k < Cv) {
+      const size_t row = (static_cast<size_t>(b) * K + n) * Cv + k;
+      if (!valid) {
+        p.kpt_proj[row * 2] = 0.f; p.kpt_proj[row * 2 + 1] = 0.f;
+        p.kpt_score[row] = 0.f;
+        p.kpt_j[row] = -1;
+        if (p.verts_cv) { p.verts_cv[row * 2] = 0.f; p.verts_cv[row * 2 + 1] = 0.f; }
+      } else {
+        const float* cand = s_xy + static_cast<size_t>(k) * KP * 2;
+        // (x, y) pairs go through the packed fp32x2 pipe (IEEE round-to-nearest per lane, the same results as the scalar
+        // ops, half the instructions).  Four independent (best, index) chains over j = 4i + u keep the compare/select
+        // dependency off the critical path; merged with torch.argmin's first-minimal-index rule.
+        const unsigned long long* cand2 = reinterpret_cast<const unsigned long long*>(cand);
+        const unsigned long long m2 = pack2(mx, my), o2 = pack2(ox, oy);
+        auto dist = [&](int j) {
+          const unsigned long long df = sub2(sub2(cand2[j], m2), o2);      // (v - m) - off      (models/model.py:147,149)
+          const unsigned long long sq = mul2(df, df);
+          return __fadd_rn(__uint_as_float(static_cast<uint32_t>(sq)), __uint_as_float(static_cast<uint32_t>(sq >> 32)));
+        };
+        float bd[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+        int bi[4] = {0, 0, 0, 0};
+        int j = 0;
+#pragma unroll 2
+        for (; j + 4 <= K; j += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float dd = dist(j + u);
+            if (dd < bd[u]) { bd[u] = dd; bi[u] = j + u; }
+          }
+        }
+        for (; j < K; ++j) {
+          const float dd = dist(j);
+          if (dd < bd[0]) { bd[0] = dd; bi[0] = j; }      // (j is past every index chain 0 has seen)
+        }
+        float best = bd[0];
+        int bj = bi[0];
+#pragma unroll
+        for (int u = 1; u < 4; ++u)
+          if (bd[u] < best || (bd[u] == best && bi[u] < bj)) { best = bd[u]; bj = bi[u]; }
+        p.kpt_proj[row * 2] = __fmul_rn(p.down, cand[2 * bj]);
+        p.kpt_proj[row * 2 + 1] = __fmul_rn(p.down, cand[2 * bj + 1]);
+        p.kpt_score[row] = sp.kscore[(static_cast<size_t>(b) * Cv + k) * K + bj];
+        p.kpt_j[row] = bj;
+        if (p.verts_cv) { p.verts_cv[row * 2] = vx; p.verts_cv[row * 2 + 1] = vy; }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- (3) per detection: class, centre, 2D box over the regressed vertices (models/model.py:70-73)
+  for (int n = n0 + tid; n < n1; n += kPostThreads) {
+    const size_t row = static_cast<size_t>(b) * K + n;
+    const int nl = n - n0;
+    const bool valid = n < n_det;
+    float lo_x = 0.f, lo_y = 0.f, hi_x = 0.f, hi_y = 0.f;
+    int c = -1;
+    if (valid) {
+      c = s_det[n].flat / HW;
+      lo_x = lo_y = INFINITY; hi_x = hi_y = -INFINITY;
+      for (int v = 0; v < V; ++v) {
+        const float vx = s_v[(nl * V + v) * 2], vy = s_v[(nl * V + v) * 2 + 1];
+        lo_x = fminf(lo_x, vx); hi_x = fmaxf(hi_x, vx);
+        lo_y = fminf(lo_y, vy); hi_y = fmaxf(hi_y, vy);
+      }
+    }
+    p.cls[row] = c;
+    p.proj[row * 2] = valid ? __fmul_rn(p.down, s_det[n].mx) : 0.f;
+    p.proj[row * 2 + 1] = valid ? __fmul_rn(p.down, s_det[n].my) : 0.f;
+    p.bbox[row * 4 + 0] = lo_x; p.bbox[row * 4 + 1] = lo_y; p.bbox[row * 4 + 2] = hi_x; p.bbox[row * 4 + 3] = hi_y;
+  }
+}
+
+static int select_post_ns(int K) {
+  int ns = 4 * next_pow2(K);
+  return ns < 1024 ? 1024 : ns;
+}
+size_t select_post_smem(int Cv, int K, int n_vert) {
+  const size_t per = static_cast<size_t>((K + kPostSplit - 1) / kPostSplit);
+  return static_cast<size_t>(select_post_ns(K)) * 8 + (static_cast<size_t>(Cv) * (K + 1) * 2 + per * n_vert * 2) * sizeof(float) +
+         static_cast<size_t>(K) * sizeof(PostDet) + 16;
+}
+
+int launch_select_post(const SelectPostParams& p, int dtype, cudaStream_t s) {
+  const size_t smem = select_post_smem(p.post.Cv, p.post.K, p.post.n_vert);
+  const unsigned grid = static_cast<unsigned>(p.post.B) * kPostSplit;
+  const int ns = select_post_ns(p.post.K);
+  static bool attr_set[64][2] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int di = dtype == 0 ? 0 : 1;
+  if (dev < 0 || dev >= 64 || !attr_set[dev][di]) {
+    cudaError_t e = dtype == 0 ? cudaFuncSetAttribute(select_post_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+                               : cudaFuncSetAttribute(select_post_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    if (dev >= 0 && dev < 64) attr_set[dev][di] = true;
+  }
+  if (dtype == 0) select_post_kernel<float><<<grid, kPostThreads, smem, s>>>(p, ns);
+  else select_post_kernel<__nv_bfloat16><<<grid, kPostThreads, smem, s>>>(p, ns);
+  return static_cast<int>(cudaGetLastError());
 }
 
 size_t post_fused_smem(int Cv, int K, int n_vert) {

@@ -47,6 +47,17 @@ struct PostFusedParams {
   float* kxy;                                                 // Tier B candidates
   float* kpt_proj; float* kpt_score; int32_t* kpt_j; float* verts_cv;   // grouping (verts_cv may be null)
 };
+// Selection + everything after it in ONE kernel (a cluster of four CTAs per image): the candidate lists of the scan kernel
+// are merged, converted to scores and sorted here (select_common.cuh), then the Tier B / Tier A epilogues and the grouping.
+struct SelectPostParams {
+  const unsigned long long* cand; const uint32_t* cand_count;
+  int Sp, list_cap;
+  float thresh;
+  float* score; int32_t* flat; int32_t* counts; float* kscore; int32_t* kflat;     // the selection (written here)
+  PostFusedParams post;                                                             // maps, shapes, outputs of the epilogues
+};
+size_t select_post_smem(int Cv, int K, int n_vert);
+int launch_select_post(const SelectPostParams& p, int dtype, cudaStream_t s);
 size_t post_fused_smem(int Cv, int K, int n_vert);
 int launch_post_fused(const PostFusedParams& p, int dtype, cudaStream_t s);
 int launch_group(const GroupParams& p, int dtype, cudaStream_t s);

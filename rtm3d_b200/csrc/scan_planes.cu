@@ -370,7 +370,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_planes_kernel(const Scan
       float tw = INFINITY;
       {
         const uint32_t halo_bytes = static_cast<uint32_t>(d.top_halo) * g.row_bytes;
-        uint32_t lane_off = view.strip_off + halo_bytes + static_cast<uint32_t>(lane_g) * 16u;   // ring offset of this thread's first group
+        // ring offset of this thread's first group (threads beyond the strip's last group read that one: never used)
+        uint32_t lane_off = view.strip_off + halo_bytes + static_cast<uint32_t>(min(lane_g, G - 1)) * 16u;
         if (lane_off >= view.ring_bytes) lane_off -= view.ring_bytes;
         const int n_full = G / kScanConsumers;
         const int n_mine = n_full + ((lane_g < G - n_full * kScanConsumers) ? 1 : 0);           // register rows in which this thread has a group
@@ -386,15 +387,16 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_planes_kernel(const Scan
           }
         };
         auto load_reg = [&](int r) {
-          // (branch-free: a register row without a group of this thread still reads a valid address of the ring)
-          uint32_t o = lane_off + static_cast<uint32_t>(r) * (kScanConsumers * 16u);
+          // (branch-free: a register row without a group of this thread re-reads the thread's first group)
+          const bool mine = r < n_mine;
+          uint32_t o = lane_off + (mine ? static_cast<uint32_t>(r) * (kScanConsumers * 16u) : 0u);
           if (o >= view.ring_bytes) o -= view.ring_bytes;
           float v[E];
           Grp<T>::load(ring + o, v);
           float mx = v[0];
 #pragma unroll
           for (int i = 1; i < E; ++i) mx = fmaxf(mx, v[i]);
-          return (r < n_mine) ? mx : -INFINITY;
+          return mine ? mx : -INFINITY;
         };
         wait_chunks(chunks_a);
 #pragma unroll

@@ -5,6 +5,7 @@
 // score / flat / counts (Tier A) or kscore / kflat with the 0.0-score fillers (Tier B).
 #include "common.cuh"
 #include "params.h"
+#include "select_common.cuh"
 
 namespace rtm3d {
 
@@ -42,64 +43,42 @@ static __device__ __noinline__ void warp_fill_kpt(const SelectParams& p, size_t 
   }
 }
 
-__global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p, int n_max) {
+__global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p, int ns) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int K = p.K, kpad = next_pow2(K), tid = threadIdx.x;
-  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);                  // [n_max]
-  uint64_t* best = keys + n_max;                                           // [kpad]
-  uint32_t* hist = reinterpret_cast<uint32_t*>(best + kpad);               // [264]
-  uint32_t* scratch = hist + 264;                                          // [3K+8]
+  __shared__ uint32_t s_n;
+  const int K = p.K, tid = threadIdx.x;
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);                  // [ns] sort buffer
+  uint32_t* scratch = reinterpret_cast<uint32_t*>(keys + ns);              // [3K+8]
   const int n_main = p.C > 0 ? p.B : 0;
   const int q = blockIdx.x;
   const bool is_main = q < n_main;
   const int first = is_main ? q * p.C * p.Sp : (p.B * p.C + (q - n_main)) * p.Sp;
   const int n_lists = is_main ? p.C * p.Sp : p.Sp;
-  // gather the lists; (logit, index) keys become (score, index) keys here, pixels at or below the score floor drop out
-  // (strict `score > thresh` of models/model.py:91; 0.0 for the keypoint planes: zero-score pixels are fillers, not peaks)
-  __shared__ uint32_t s_n;
-  if (tid == 0) s_n = 0u;
-  __syncthreads();
-  const float lim = is_main ? p.thresh : 0.0f;
-  for (int l = 0; l < n_lists; ++l) {
-    const uint32_t raw = p.cand_count[first + l];
-    const int cnt = static_cast<int>(raw & ~kCandScoreKeys);
-    const bool score_keys = (raw & kCandScoreKeys) != 0u;
-    const unsigned long long* src = p.cand + static_cast<size_t>(first + l) * p.list_cap;
-    for (int i = tid; i < cnt; i += kSelThreads) {
-      unsigned long long k = src[i];
-      bool valid = true;
-      if (!score_keys) {
-        const float sc = sigmoid_ref(f32_unord(static_cast<uint32_t>(k >> 32)));
-        valid = sc > lim;
-        k = make_key(sc, key_flat(k));
-      }
-      if (valid) keys[atomicAdd(&s_n, 1u)] = k;
-    }
-  }
-  __syncthreads();
-  const int n = static_cast<int>(s_n);
-  const int have = block_select_topk(keys, n, K, best, hist);
-  for (int i = have + tid; i < kpad; i += kSelThreads) best[i] = 0ull;
-  __syncthreads();
-  block_bitonic_sort_desc(best, kpad);
+  // strict `score > thresh` of models/model.py:91; 0.0 for the keypoint planes: zero-score pixels are fillers, not peaks
+  const int have = block_select_sorted<kSelThreads>(p.cand, p.cand_count, p.list_cap, first, n_lists, K, is_main ? p.thresh : 0.0f, keys, ns, &s_n);
   if (is_main) {
-    // every key of a main list has score > thresh already (models/model.py:91): counts = number of keys
+    // every key of a main list has score > thresh: counts = number of keys
     const int b = q;
     for (int j = tid; j < K; j += kSelThreads) {
       const size_t row = static_cast<size_t>(b) * K + j;
       const bool valid = j < have;
-      p.score[row] = valid ? key_score(best[j]) : 0.f;
-      p.flat[row] = valid ? static_cast<int32_t>(key_flat(best[j])) : -1;
+      p.score[row] = valid ? key_score(keys[j]) : 0.f;
+      p.flat[row] = valid ? static_cast<int32_t>(key_flat(keys[j])) : -1;
     }
     if (tid == 0) p.counts[b] = have;
   } else if (tid < 32) {
-    warp_fill_kpt(p, static_cast<size_t>(q - n_main) * K, best, have, scratch, tid);
+    warp_fill_kpt(p, static_cast<size_t>(q - n_main) * K, keys, have, scratch, tid);
   }
 }
 
+static int select_ns(int K) {
+  int ns = 4 * next_pow2(K);
+  return ns < 1024 ? 1024 : ns;
+}
+
 size_t select_smem_bytes(int C, int Cv, int Sp, int list_cap, int K) {
-  const int lists = (C > 0 ? C : 1) * Sp;
-  return static_cast<size_t>(lists) * list_cap * 8 + static_cast<size_t>(next_pow2(K)) * 8 + 264 * 4 + (3 * static_cast<size_t>(K) + 8) * 4;
+  (void)C; (void)Cv; (void)Sp; (void)list_cap;       // lists that do not fit the sort buffer are merged in rounds
+  return static_cast<size_t>(select_ns(K)) * 8 + (3 * static_cast<size_t>(K) + 8) * 4;
 }
 
 int launch_select(const SelectParams& p, cudaStream_t s) {
@@ -112,9 +91,8 @@ int launch_select(const SelectParams& p, cudaStream_t s) {
     if (e != cudaSuccess) return static_cast<int>(e);
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  const int n_max = (p.C > 0 ? p.C : 1) * p.Sp * p.list_cap;
   const unsigned grid = static_cast<unsigned>((p.C > 0 ? p.B : 0) + p.B * p.Cv);
-  select_kernel<<<grid, kSelThreads, smem, s>>>(p, n_max);
+  select_kernel<<<grid, kSelThreads, smem, s>>>(p, select_ns(p.K));
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -305,17 +305,22 @@ class HeatmapDecoder:
             else:
                 det, cand, grp = cached
             mark()
+            legacy = bool(self.flags & (_native.FLAG_LEGACY_PLANES | _native.FLAG_FORCE_GENERIC))
+            # marks: the same two launches as the unmarked call, issued separately with an event in between -- scan kernel, then
+            # select + post kernel (legacy / generic kernels: selection, then rtm3d_post_fused)
+            stage_flags = 0
+            if marks is not None:
+                stage_flags = (_native.FLAG_NO_GROUP | _native.FLAG_NO_EPILOGUE) if legacy else _native.FLAG_NO_SELECT
             rc = self._lib.rtm3d_decode_fused(
                 main.data_ptr(), off.data_ptr(), off2.data_ptr(), kpt_logits.data_ptr(), voff2.data_ptr(), dt,
                 B, C, Cv, H, W, V, K, self.score_thresh, self.down_sample,
                 det.cls.data_ptr(), det.score.data_ptr(), det.proj.data_ptr(), det.verts.data_ptr(), det.bbox.data_ptr(),
                 det.flat.data_ptr(), det.counts.data_ptr(), cand.score.data_ptr(), cand.xy.data_ptr(), cand.flat.data_ptr(),
                 grp.kpt_proj.data_ptr(), grp.kpt_score.data_ptr(), grp.kpt_j.data_ptr(), grp.verts.data_ptr(),
-                ws.data_ptr(), ws.numel(),
-                self.flags | ((_native.FLAG_NO_GROUP | _native.FLAG_NO_EPILOGUE) if marks is not None else 0), stream)
+                ws.data_ptr(), ws.numel(), self.flags | stage_flags, stream)
             mark()
             _native.check(rc, "rtm3d_decode_fused")
-            if marks is not None:
+            if marks is not None and legacy:
                 rc = self._lib.rtm3d_post_fused(
                     det.flat.data_ptr(), det.counts.data_ptr(), cand.flat.data_ptr(), cand.score.data_ptr(),
                     off.data_ptr(), off2.data_ptr(), voff2.data_ptr(), dt, B, C, Cv, H, W, V, K, self.down_sample,
@@ -323,6 +328,15 @@ class HeatmapDecoder:
                     grp.kpt_proj.data_ptr(), grp.kpt_score.data_ptr(), grp.kpt_j.data_ptr(), grp.verts.data_ptr(), stream)
                 mark()
                 _native.check(rc, "rtm3d_post_fused")
+            elif marks is not None:
+                rc = self._lib.rtm3d_select_post(
+                    off.data_ptr(), off2.data_ptr(), voff2.data_ptr(), dt, B, C, Cv, H, W, V, K, self.score_thresh, self.down_sample,
+                    det.cls.data_ptr(), det.score.data_ptr(), det.proj.data_ptr(), det.verts.data_ptr(), det.bbox.data_ptr(),
+                    det.flat.data_ptr(), det.counts.data_ptr(), cand.score.data_ptr(), cand.xy.data_ptr(), cand.flat.data_ptr(),
+                    grp.kpt_proj.data_ptr(), grp.kpt_score.data_ptr(), grp.kpt_j.data_ptr(), grp.verts.data_ptr(),
+                    ws.data_ptr(), ws.numel(), self.flags, stream)
+                mark()
+                _native.check(rc, "rtm3d_select_post")
         return det, cand, grp
 
     # ------------------------------------------------------------------ Tier C
