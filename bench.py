@@ -1,20 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- decoded images/sec of the RTM3D keypoint-heatmap decode path on B200 (+ fraction of the HBM roofline).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4] [--impl b200|reference] [--scaling weak|strong]
+                    [--dtype f32|bf16] [--graph] [--verify]
 
 A "step" = one pass of the hot path (Tier A main decode + Tier B keypoint decode + grouping; models/model.py:29-162)
 over one batch of synthetic head outputs that are already resident in HBM.  The default workload is BASELINE.json
 configs[3] ("cfg4": 256 images per GPU, 3x96x320 main heat-map + 9-keypoint heat-map + the 16/2/2-channel regression
-maps, K=100, thresh 0.4), the configuration the metric's "1/2/4/8 B200" is quoted on; per-GPU work is fixed as N
-grows (weak scaling, images are independent: SURVEY.md 8e) and for N > 1 the step ends with the NCCL all-gather of
-the fixed-size detections.  One JSON line is printed by rank 0 (contract in the task statement):
+maps, K=100, thresh 0.4), the configuration the metric's "1/2/4/8 B200" is quoted on.  Images are independent
+(SURVEY.md 8e): `--scaling weak` (default) keeps 256 images per GPU as N grows, `--scaling strong` cuts the 256 images into
+N shards; for N > 1 the step ends with the NCCL all-gather of the fixed-size detections.  One JSON line is printed by
+rank 0 (contract in the task statement):
 
   value        whole-job images/s, device-timed (CUDA events around exactly K steps, max over ranks)
-  roofline     dominant kernel: ALGORITHMIC bytes per launch / its CUDA-event duration vs MEASURED_PEAKS.json hbm_gbs
+  roofline     per kernel: the bytes THAT kernel moves / its CUDA-event duration vs MEASURED_PEAKS.json hbm_gbs (the
+               dominant kernel's figures at the top level); step_frac = algorithmic bytes of the whole path /
+               ms_per_step -- the honest whole-path number; cold_ms = first launch on a fresh workspace; shift_ms =
+               ms_per_step when consecutive batches come from different distributions (the kernels keep no state)
   e2e          same metric through the host-buffer C-ABI entry points (pinned host in -> pinned host out, H2D + D2H
                inside the timed region)
-  cpu_baseline the oracle's torch port of the reference decoder on the box's host cores (bounded sample), rank 0 only
+  cpu_baseline the oracle's torch port of the reference decoder on the box's host cores (bounded sample), N = 1 only
   clocks       SM clock / throttle reasons sampled with NVML while the timed region runs
 
 `--impl reference` times the reference's CPU implementation of the same path (oracle port: the reference is Python and
@@ -40,9 +45,12 @@ THRESH, DOWN = 0.4, 4.0
 CPU_SAMPLE_IMAGES = 16          # bounded CPU sample per step of the reference arm / cpu_baseline leg
 
 WORKLOADS = {
-    # name: B per GPU, C, H, W, K, keypoint channels
+    # name: B per GPU (weak scaling) = per job (strong scaling), C, H, W, K, keypoint channels, regression channels of the box decode
     "cfg2": dict(B=32, C=3, H=96, W=320, K=50, kpt=9, note="BASELINE configs[1]: DLA-34 head outputs batch 32, K=50"),
-    "cfg3": dict(B=64, C=3, H=96, W=320, K=100, kpt=0, note="BASELINE configs[2]: centre-keypoint decode batch 64, K=100 (main branch only)"),
+    "cfg2x": dict(B=64, C=3, H=96, W=320, K=100, kpt=9, note="north_star's batch >= 64 point: 64 images, main + 9-kpt heat-map, K=100"),
+    "cfg3": dict(B=64, C=3, H=96, W=320, K=100, kpt=0, reg=8,
+                 note="BASELINE configs[2]: SMOKE-style centre-keypoint decode (depth/dim/orientation regression, closed-form box) "
+                      "batch 64, K=100 -- Tier C parity unpinned (no reference code)"),
     "cfg4": dict(B=256, C=3, H=96, W=320, K=100, kpt=9, note="BASELINE configs[3]: ResNet-18 head outputs batch 256 per GPU, K=100, main + 9-kpt heat-map"),
     "cfg4main": dict(B=256, C=3, H=96, W=320, K=100, kpt=0, note="BASELINE configs[3], main branch only (what the reference's inference() runs today)"),
     "cfg5": dict(B=128, C=3, H=192, W=640, K=100, kpt=9, note="BASELINE configs[4]: 192x640 heat-maps batch 128 per GPU, K=100, main + 9-kpt heat-map"),
@@ -53,9 +61,20 @@ def algorithmic_bytes_per_image(w, elem=4, n_vert=8):
     """A = C_hm*H*W*e + K*C_reg*32 + out (gathers charged one 32-byte sector per scalar; regression planes
     are NOT counted in full).  Returns (total, main part, keypoint part)."""
     HW, K, Cv = w["H"] * w["W"], w["K"], w["kpt"]
+    if w.get("reg"):      # cfg3: C_reg regression channels gathered at the K peaks, 128 B of box parameters per detection
+        main = w["C"] * HW * elem + K * w["reg"] * 32 + K * 128 + 4
+        return main, main, 0
     main = w["C"] * HW * elem + K * (2 * n_vert + 2) * 32 + K * 100 + 4
     kpt = (Cv * HW * elem + Cv * K * 2 * 32 + K * Cv * 12) if Cv else 0
     return main + kpt, main, kpt
+
+
+def kernel_bytes_per_image(w, elem=4, n_vert=8):
+    """The bytes each kernel of the path moves per image (what its own roofline fraction is computed from): the scan kernel
+    streams the heat-maps once; everything else (gathers at 32 B per scalar, outputs) belongs to the kernels behind it."""
+    total, _, _ = algorithmic_bytes_per_image(w, elem, n_vert)
+    heat = (w["C"] + w["kpt"]) * w["H"] * w["W"] * elem
+    return {"scan": heat, "post": total - heat}
 
 
 def ncu_traffic(workload):
@@ -128,14 +147,22 @@ class ClockSampler(threading.Thread):
 
 def make_inputs(torch, w, device, seed, kind="randn", dtype="f32"):
     """every head map torch.randn from a seeded generator on the owning device.  dtype "bf16": the maps as
-    a bf16-emitting head would hand them over; the decode widens them exactly and computes in fp32."""
+    a bf16-emitting head would hand them over; the decode widens them exactly and computes in fp32.
+    kind "trained": the heat-maps as randn*3 - 6 (sparse, "trained-like": the shift variant alternates it with randn).
+    Workloads with `reg` (cfg3): third return value = (regression map [B,reg,H,W], camera matrices [B,9], dim_ref [C,3])."""
     g = torch.Generator(device=device).manual_seed(seed)
     B, C, H, W = w["B"], w["C"], w["H"], w["W"]
     td = torch.bfloat16 if dtype == "bf16" else torch.float32
-    mk = lambda c: torch.randn((B, c, H, W), generator=g, device=device, dtype=torch.float32).to(td)
-    logits = [mk(C), mk(16), mk(2), mk(2)]
-    kpt = mk(w["kpt"]) if w["kpt"] else None
-    return logits, kpt
+    raw = lambda c: torch.randn((B, c, H, W), generator=g, device=device, dtype=torch.float32)
+    heat = (lambda c: raw(c) * 3 - 6) if kind == "trained" else raw
+    logits = [heat(C).to(td), raw(16).to(td), raw(2).to(td), raw(2).to(td)]
+    kpt = heat(w["kpt"]).to(td) if w["kpt"] else None
+    box = None
+    if w.get("reg"):
+        cam = torch.tensor([721.54 / 4, 0, 609.56 / 4, 0, 721.54 / 4, 172.85 / 4, 0, 0, 1], dtype=torch.float32, device=device)
+        dim_ref = torch.tensor([[1.53, 1.63, 3.88], [1.76, 0.66, 0.84], [1.74, 0.60, 1.76]], dtype=torch.float32, device=device)[:C]
+        box = (raw(w["reg"]).to(td), cam.repeat(B, 1).contiguous(), dim_ref.contiguous())
+    return logits, kpt, box
 
 
 def cpu_reference_step(torch, decode_ref, logits, kpt, K):
@@ -150,7 +177,7 @@ def time_cpu_reference(torch, w, steps, warmup, seed=1234):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     ws = dict(w, B=min(w["B"], CPU_SAMPLE_IMAGES))
-    logits, kpt = make_inputs(torch, ws, torch.device("cpu"), seed)
+    logits, kpt, _ = make_inputs(torch, ws, torch.device("cpu"), seed)
     with torch.no_grad():
         for _ in range(warmup):
             cpu_reference_step(torch, decode_ref, logits, kpt, w["K"])
@@ -161,10 +188,19 @@ def time_cpu_reference(torch, w, steps, warmup, seed=1234):
     return ws["B"] * steps / dt, dt / steps * 1e3, cores, torch.get_num_threads(), ws["B"]
 
 
-def config_dict(name, w, n_gpus):
-    return {"workload": f"{name}: {w['note']}", "images_per_gpu": w["B"], "global_images": w["B"] * n_gpus,
+def config_dict(name, w, n_gpus, scaling, images_per_gpu):
+    """The workload, identical in both arms (the driver compares the two dicts)."""
+    return {"workload": f"{name}: {w['note']}", "images_per_gpu": images_per_gpu, "global_images": images_per_gpu * n_gpus,
             "heatmap": [w["C"], w["H"], w["W"]], "kpt_channels": w["kpt"], "topk": w["K"], "score_thresh": THRESH,
-            "down_sample": DOWN, "parallelism": f"image-sharded x{n_gpus}"}
+            "down_sample": DOWN, "parallelism": f"image-sharded x{n_gpus} ({scaling} scaling)"}
+
+
+def images_per_gpu(w, n_gpus, scaling):
+    if scaling == "strong":
+        if w["B"] % n_gpus:
+            raise SystemExit(f"bench.py: --scaling strong needs the workload's {w['B']} images to divide by {n_gpus} GPUs")
+        return w["B"] // n_gpus
+    return w["B"]
 
 
 def run_reference(args, w):
@@ -174,8 +210,8 @@ def run_reference(args, w):
     import torch
     ips, ms, cores, threads, nb = time_cpu_reference(torch, w, args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": round(ips, 2), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": config_dict(args.workload, w, args.gpus),
+            "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_dict(args.workload, w, args.gpus, args.scaling, images_per_gpu(w, args.gpus, args.scaling)),
             "cpu_baseline": {"value": round(ips, 2), "unit": UNIT, "cores": cores, "kind": "port", "torch_threads": threads,
                              "sample": f"{nb} images of the workload per step (torch port of Model.inference incl. the clone of "
                                        f"models/model.py:27 and the keypoint branch when the workload has one), {args.steps} steps"},
@@ -185,19 +221,29 @@ def run_reference(args, w):
     return 0
 
 
-def run_b200(args, w):
-    import torch
-    import torch.distributed as dist
-    from rtm3d_b200 import HeatmapDecoder, HostDecodeSession
-    from rtm3d_b200.decoder import PackedDetections
-
+def run_b200(args, w_job):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (rtm3d_b200 has no CPU path; use --impl reference for the CPU arm)")
     if world != args.gpus:
         raise SystemExit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch N>1 with torch.distributed.run")
+    B = images_per_gpu(w_job, world, args.scaling)
+    w = dict(w_job, B=B)
+
+    # ---- CPU baseline first (N = 1 only): before any CUDA / NCCL work competes for the host cores
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        ips, ms, cores, threads, nb = time_cpu_reference(torch, w_job, steps=3, warmup=1)
+        cpu_baseline = {"value": round(ips, 2), "unit": UNIT, "cores": cores, "kind": "port", "torch_threads": threads,
+                        "sample": f"{nb} images of the workload, 1 warm-up + 3 timed passes of the torch port of "
+                                  "Model.inference (incl. the clone of models/model.py:27 and the keypoint branch)"}
+
+    import torch.distributed as dist
+    from rtm3d_b200 import HeatmapDecoder, HostDecodeSession
+    from rtm3d_b200.decoder import PackedDetections
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     saved_stdout = None
@@ -208,39 +254,58 @@ def run_b200(args, w):
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
-    K, B, Cv = w["K"], w["B"], w["kpt"]
-    # N > 1: the all-gather's NCCL kernel runs beside the next batch's decode; the persistent plane kernel leaves it a few
+    K, Cv = w["K"], w["kpt"]
+    # N > 1: the all-gather's NCCL kernel runs beside the next batch's decode; the persistent scan kernel leaves it a few
     # SMs instead of queueing its last CTAs behind it (--max-ctas; 0 = one CTA per SM)
     max_ctas = args.max_ctas if args.max_ctas >= 0 else (0 if world == 1 else 144)
     # result buffers are reused from call to call (saves ~35 us of host time per step); at N > 1 two decoders alternate so
     # that a batch's results stay untouched while the gather stream packs them
-    decs_dev = [HeatmapDecoder(THRESH, K, DOWN, max_ctas=max_ctas, reuse_outputs=True) for _ in range(1 if world == 1 else 2)]
-    dec = decs_dev[0]
+    mk_dec = lambda: HeatmapDecoder(THRESH, K, DOWN, max_ctas=max_ctas, reuse_outputs=True)
+    decs_dev = [mk_dec() for _ in range(1 if world == 1 else 2)]
     nsets = 2
     sets = [make_inputs(torch, w, dev, 1234 + rank + 100 * s, dtype=args.dtype) for s in range(nsets)]
     elem = 2 if args.dtype == "bf16" else 4
     heat_bytes = B * (w["C"] + Cv) * w["H"] * w["W"] * elem
-    # kernels per step: plane-streaming kernel + fused post kernel (main only: + Tier A epilogue)
-    launches_per_step = 2 + (1 if world > 1 else 0)    # + the wire-packing kernel of the gather
-    marks_per_step = 3 if Cv else 2          # events: before, after the plane kernel, after the post kernel
+    if w.get("reg"):
+        names = ["scan+select(main)", "box3d"]
+    elif Cv:
+        names = ["scan_planes(main+kpt)", "select_post"]
+    else:
+        names = ["scan+select+epilogue(main)"]
+    launches_per_step = {"scan_planes(main+kpt)": 1, "select_post": 1, "scan+select(main)": 2, "box3d": 1, "scan+select+epilogue(main)": 3}
+    n_launches = sum(launches_per_step[n] for n in names) + (1 if world > 1 else 0)    # + the wire-packing kernel of the gather
 
     gather_out = None
 
-    def step(i, marks=None):
+    def decode(i, dec, inputs, marks=None):
+        logits, kpt, box = inputs
+
+        def mark():
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append(e)
+        if box is not None:
+            mark()
+            det = dec.select_main(logits[0])
+            mark()
+            dec.decode_box3d(det, box[0], box[1], box[2], w["C"], cached=True)
+            mark()
+            return det
+        if Cv:
+            det, _, _ = dec.decode_with_keypoints(logits, kpt, marks=marks)
+            return det
+        mark()
+        det = dec.decode_packed(logits)
+        mark()
+        return det
+
+    def step(i, marks=None, inputs=None):
         nonlocal gather_out
-        logits, kpt = sets[i % nsets]
         dec = decs_dev[i % len(decs_dev)]
         if world > 1 and gather_out is not None and gather_out["packed"][i & 1] is not None:
             torch.cuda.current_stream().wait_event(gather_out["packed"][i & 1])      # batch i-2's results have been packed
-        if Cv:
-            det, cand, grp = dec.decode_with_keypoints(logits, kpt, marks=marks)
-        else:
-            if marks is not None:
-                e = torch.cuda.Event(enable_timing=True); e.record(); marks.append(e)
-            det = dec.decode_packed(logits)
-            if marks is not None:
-                e = torch.cuda.Event(enable_timing=True); e.record(); marks.append(e)
-            grp = None
+        det = decode(i, dec, inputs if inputs is not None else sets[i % nsets], marks)
         if world > 1:
             # the path's one collective: pack (one launch of the library) + all-gather of the fixed-size
             # detections.  It runs on a second stream behind an event, so the gather of batch i overlaps the decode of
@@ -260,7 +325,7 @@ def run_b200(args, w):
                     gather_out["packed"][slot] = torch.cuda.Event()
                 gather_out["packed"][slot].record()
                 dist.all_gather_into_tensor(gather_out["full"][slot], wire)
-        return det, grp
+        return det
 
     def barrier():
         if world > 1:
@@ -273,13 +338,32 @@ def run_b200(args, w):
     for i in range(args.warmup):
         step(i)
     barrier()
+
+    # ---- optional: the step captured in CUDA graphs (one per input set), replayed in the timed region
+    graphs = None
+    if args.graph:
+        if world > 1:
+            raise SystemExit("bench.py: --graph is a single-GPU option (the gather stream is not captured)")
+        graphs = []
+        for s in range(nsets):
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph):
+                step(s)
+            graphs.append(gph)
+        for s in range(nsets):
+            graphs[s].replay()
+        barrier()
+
     # ---- timed region: exactly K steps, CUDA events on the launching stream, per-kernel marks on the same stream
-    marks = []
+    marks = [] if graphs is None else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     e0.record()
     for i in range(args.steps):
-        step(i, marks)
+        if graphs is None:
+            step(i, marks)
+        else:
+            graphs[i % nsets].replay()
     e1.record()
     barrier()
     t_wall1 = time.perf_counter()
@@ -290,21 +374,77 @@ def run_b200(args, w):
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
 
-    # per-kernel durations from the marks (each step: before, after main, [after kpt, after group])
-    per = marks_per_step
-    names = ["decode_planes(main+kpt)", "post_fused"] if Cv else ["decode_planes(main)+epilogue"]
-    kernel_ms = {n: 0.0 for n in names}
-    for s in range(args.steps):
-        for j, n in enumerate(names):
-            kernel_ms[n] += marks[s * per + j].elapsed_time(marks[s * per + j + 1])
-    kernel_ms = {n: v / args.steps for n, v in kernel_ms.items()}
+    # per-kernel durations from the marks (each step: one event before every stage and one after the last)
+    kernel_ms = {}
+    if marks is not None:
+        per = len(names) + 1
+        kernel_ms = {n: 0.0 for n in names}
+        for s in range(args.steps):
+            for j, n in enumerate(names):
+                kernel_ms[n] += marks[s * per + j].elapsed_time(marks[s * per + j + 1])
+        kernel_ms = {n: v / args.steps for n, v in kernel_ms.items()}
+    else:                                   # --graph: per-kernel times from a short un-captured run afterwards
+        m2 = []
+        for i in range(8):
+            step(i, m2)
+        torch.cuda.synchronize()
+        per = len(names) + 1
+        kernel_ms = {n: sum(m2[s * per + j].elapsed_time(m2[s * per + j + 1]) for s in range(8)) / 8 for j, n in enumerate(names)}
+
+    # ---- the gather delivers every rank's detections to every rank: check the last two batches on this rank
+    verify = None
+    if world > 1 and args.verify:
+        torch.cuda.synchronize()
+        ok = True
+        for slot in range(2):
+            full, mine = gather_out["full"][slot], gather_out["mine"][slot]
+            ok &= bool(torch.equal(full[rank * B:(rank + 1) * B], mine))                  # my block is my own wire rows
+            sums = full.view(world, -1).to(torch.int64).sum(dim=1)                        # checksum of every rank's block as I received it
+            own = torch.zeros(world, dtype=torch.int64, device=dev)
+            own[rank] = mine.to(torch.int64).sum()
+            dist.all_reduce(own, op=dist.ReduceOp.SUM)                                     # the checksums the owners computed
+            ok &= bool(torch.equal(sums, own))
+            # ... and the rows decode back into detections with plausible counts
+            back = PackedDetections.from_wire(full, K)
+            ok &= bool(((back.counts >= 0) & (back.counts <= K)).all())
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        verify = {"ok": bool(flag.item()), "ranks": world, "rows_per_rank": B,
+                  "what": "all-gathered wire rows == every owner's rows (own block bit-equal, all blocks by checksum), last two batches"}
+
+    # ---- the kernels keep no state: first launch on a fresh workspace, and batches that alternate between two distributions
+    cold_ms = shift_ms = None
+    if world == 1 and not args.no_extras:
+        # cold: every workspace of the decoder re-initialised (rtm3d_workspace_init: zeroed + tables), then ONE step
+        from rtm3d_b200 import _native
+        for wsb in decs_dev[0]._ws.values():
+            _native.check(_native.lib().rtm3d_workspace_init(wsb.data_ptr(), wsb.numel(), torch.cuda.current_stream(dev).cuda_stream), "workspace_init")
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        decode(0, decs_dev[0], sets[1])
+        c1.record()
+        torch.cuda.synchronize()
+        cold_ms = c0.elapsed_time(c1)
+        shifted = [sets[0], make_inputs(torch, w, dev, 999, kind="trained", dtype=args.dtype)]
+        for i in range(4):
+            step(i, inputs=shifted[i % 2])
+        torch.cuda.synchronize()
+        n_shift = max(10, min(args.steps, 50))
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(n_shift):
+            step(i, inputs=shifted[i % 2])
+        s1.record()
+        torch.cuda.synchronize()
+        shift_ms = s0.elapsed_time(s1) / n_shift
 
     # ---- end to end: pinned host buffers in, pinned host buffers out, through the host-buffer C-ABI entry points
     # Two sessions (each with its own decoder workspace, device staging and pinned result buffers) alternate on two
     # streams: the zero-copy gathers and the D2H of step i overlap the H2D of step i+1.  Every step's H2D, kernels and
     # D2H are inside the timed region and every step's result is read on the host.
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not w.get("reg"):
         host_logits = [t.to("cpu").pin_memory() for t in sets[0][0]]
         host_kpt = sets[0][1].to("cpu").pin_memory() if Cv else None
         depth = 2
@@ -344,32 +484,42 @@ def run_b200(args, w):
 
     if rank == 0:
         peak, peak_src = peaks()
-        A, A_main, A_kpt = algorithmic_bytes_per_image(w, elem=elem)
+        A, _, _ = algorithmic_bytes_per_image(w, elem=elem)
+        kb = kernel_bytes_per_image(w, elem=elem)
+        own = {}
+        for j, n in enumerate(names):
+            own[n] = B * (kb["scan"] if j == 0 else kb["post"]) if len(names) > 1 else B * A
+        per_kernel = {n: {"ms": round(kernel_ms[n], 5), "bytes": own[n],
+                          "gbs": round(own[n] / (kernel_ms[n] * 1e-3) / 1e9, 1) if kernel_ms[n] > 0 else 0.0,
+                          "frac": round(own[n] / (kernel_ms[n] * 1e-3) / 1e9 / peak, 4) if kernel_ms[n] > 0 else 0.0} for n in names}
         dom = max(kernel_ms, key=kernel_ms.get)
-        dom_bytes = B * (A if dom.startswith("decode_planes(main+kpt)") else A_main if dom.startswith("decode_planes") else 0)
-        achieved = dom_bytes / (kernel_ms[dom] * 1e-3) / 1e9 if kernel_ms[dom] > 0 else 0.0
         step_gbs = B * A / (ms_step * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": round(B * world / (ms_step * 1e-3), 1), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 5), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if elem == 4 else "f32 (bf16 maps widened on load)", "data": "synthetic",
-            "config": dict(config_dict(args.workload, w, world),
-                           l2=f"{nsets} input sets rotated, {heat_bytes / 1e6:.0f} MB of heat-map per step vs 126 MB L2"
-                              + ("" if heat_bytes > 130e6 else " (SMALLER than L2: later steps may hit L2)")),
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
-                         "bytes_per_launch": dom_bytes, "kernel_ms": {k: round(v, 5) for k, v in kernel_ms.items()},
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32" if elem == 4 else "f32 (bf16 maps widened on load)", "data": "synthetic",
+            "config": config_dict(args.workload, w_job, world, args.scaling, B),
+            "inputs": f"{nsets} input sets rotated, {heat_bytes / 1e6:.0f} MB of heat-map per step vs 126 MB L2"
+                      + ("" if heat_bytes > 130e6 else " (SMALLER than L2: later steps may hit L2)"),
+            "run": {"cuda_graph": bool(args.graph), "max_ctas": max_ctas},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                         "frac": per_kernel[dom]["frac"], "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
+                         "bytes_per_launch": per_kernel[dom]["bytes"],
+                         "bytes_note": "the bytes the kernel itself moves: the scan kernel streams the heat-maps once; gathers (32 B per "
+                                       "scalar) and outputs belong to the kernels behind it",
+                         "kernel_ms": {k: round(v, 5) for k, v in kernel_ms.items()}, "kernels": per_kernel,
                          "step_achieved": round(step_gbs, 1), "step_frac": round(step_gbs / peak, 4),
-                         "algorithmic_bytes_per_image": A},
+                         "algorithmic_bytes_per_image": A, "cold_ms": None if cold_ms is None else round(cold_ms, 5),
+                         "shift_ms_per_step": None if shift_ms is None else round(shift_ms, 5),
+                         "state": "none: thresholds come from each strip's own data (no memory across planes or launches)"},
             "e2e": e2e,
-            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches": n_launches * args.steps,
             "clocks": sampler.summary(t_wall0, t_wall1),
         }
-        if not args.no_cpu_baseline:
-            ips, ms, cores, threads, nb = time_cpu_reference(torch, w, steps=3, warmup=1)
-            line["cpu_baseline"] = {"value": round(ips, 2), "unit": UNIT, "cores": cores, "kind": "port", "torch_threads": threads,
-                                    "sample": f"{nb} images of the workload, 1 warm-up + 3 timed passes of the torch port of "
-                                              "Model.inference (incl. the clone of models/model.py:27 and the keypoint branch)"}
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        if verify is not None:
+            line["verify"] = verify
         if saved_stdout is not None:
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
@@ -387,10 +537,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg4")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak", help="weak: the workload's batch per GPU; strong: cut into N shards")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dtype", choices=["f32", "bf16"], default="f32", help="element type of the head maps handed to the decode")
     ap.add_argument("--no-e2e", action="store_true", help="device-resident timed loop only (the ncu passes)")
-    ap.add_argument("--max-ctas", type=int, default=-1, help="CTAs of the plane-streaming kernel (-1: all SMs at N=1, 144 at N>1)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the cold-launch and distribution-shift measurements")
+    ap.add_argument("--graph", action="store_true", help="replay the step from CUDA graphs (launch-bound small batches)")
+    ap.add_argument("--verify", action="store_true", help="N > 1: check the all-gathered detections against every owner's rows")
+    ap.add_argument("--max-ctas", type=int, default=-1, help="CTAs of the scan kernel (-1: all SMs at N=1, 144 at N>1)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -95,6 +95,14 @@ int rtm3d_decode_main(const void* hm, const void* off, const void* off2, int dty
                       void* ws, size_t ws_bytes, unsigned flags, void* stream);
 
 /*
+ * Selection only: the first half of rtm3d_decode_main (models/model.py:77-98 without the gathers): score f32 [B,K],
+ * flat int32 [B,K] (c*H*W + y*W + x, -1 beyond counts[b]) and counts int32 [B].  For callers with their own epilogue behind
+ * the peaks -- rtm3d_decode_box3d (depth / dimension / orientation regression, BASELINE configs[2]).
+ */
+int rtm3d_select_main(const void* hm, int dtype, int B, int C, int H, int W, int K, float thresh,
+                      float* score, int32_t* flat, int32_t* counts, void* ws, size_t ws_bytes, unsigned flags, void* stream);
+
+/*
  * Same computation for HOST-resident head outputs (the e2e path of bench.py).  `hm_host` is copied to `dev_hm`
  * (device staging of B*C*H*W elements) with one async copy; `off_host` / `off2_host` must be page-locked, mapped
  * host memory (cudaHostAlloc / cudaHostRegister): only the K*(2*n_vert+2) scalars per image that the decode needs

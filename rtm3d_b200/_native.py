@@ -13,6 +13,7 @@ CSRC = os.path.join(_HERE, "csrc")
 ABI_VERSION = 1
 
 F32, BF16 = 0, 1
+ERR_SHAPE = -2
 FLAG_FORCE_GENERIC = 1
 FLAG_NO_SPECULATION = 2
 FLAG_NO_GROUP = 4
@@ -31,6 +32,7 @@ SIGNATURES = {
     "rtm3d_decode_workspace_bytes": [_i, _i, _i, _i, _i, _c.POINTER(_sz)],
     "rtm3d_workspace_init": [_vp, _sz, _vp],
     "rtm3d_decode_main": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _u, _vp],
+    "rtm3d_select_main": [_vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _sz, _u, _vp],
     "rtm3d_decode_main_host": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp,
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _u, _vp],

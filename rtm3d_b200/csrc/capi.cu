@@ -98,6 +98,9 @@ int scan_and_select(const rtm3d::PlaneParams& q, const rtm3d::WorkspaceLayout& L
   // the lists of this call must fit the workspace
   const int sp_default = rtm3d::scan_strips_per_plane(q.H, q.W, q.K, dtype, strips_override);
   if (sp_default <= 0 || static_cast<long long>(q.B) * (q.C + q.Cv) * sp_default > L.cand_strips || rtm3d::scan_list_cap(q.K) > L.cand_cap) return -1000;
+  // planes that do not fit the ring as ONE strip: every strip has to supply its own K best, which multiplies the candidates;
+  // the streaming kernel of round 1 is the faster one there (unless the caller forces a number of strips)
+  if (strips_override == 0 && sp_default > 1) return -1000;
   if (rtm3d::select_smem_bytes(q.C, q.Cv, sp_default, rtm3d::scan_list_cap(q.K), q.K) > 200 * 1024) return -1000;
   int Sp = 0, cap = 0;
   const int rc = rtm3d::launch_scan(sp, dtype, strips_override, static_cast<int>((flags >> 16) & 0xFFu), static_cast<int>((flags >> 24) & 0xFu), s, &Sp, &cap);
@@ -105,7 +108,7 @@ int scan_and_select(const rtm3d::PlaneParams& q, const rtm3d::WorkspaceLayout& L
   if (int e = cuda_fail(rc, "decode (scan kernel) launch")) return e;
   if (flags & RTM3D_FLAG_NO_SELECT) return 0;                       // the caller continues with rtm3d_select_post (bench.py's marks)
   if (post) {
-    rtm3d::SelectPostParams f{sp.cand, sp.cand_count, Sp, cap, q.thresh, q.score, q.flat, q.counts, q.kscore, q.kflat, *post};
+    rtm3d::SelectPostParams f{sp.cand, sp.cand_count, Sp, cap, q.thresh, q.score, q.flat, q.counts, q.kscore, q.kflat, *post, sp.stats};
     return cuda_fail(rtm3d::launch_select_post(f, dtype, s), "decode (select + post kernel) launch");
   }
   rtm3d::SelectParams sel{sp.cand, sp.cand_count, q.B, q.C, q.Cv, q.H, q.W, q.K, Sp, cap, q.thresh, q.score, q.flat, q.counts, q.kscore, q.kflat};
@@ -136,9 +139,11 @@ int dispatch(rtm3d::DecodeParams& p, const rtm3d::WorkspaceLayout& L, int dtype,
     if (!(flags & RTM3D_FLAG_LEGACY_PLANES)) {
       rc = scan_and_select(q, L, reinterpret_cast<unsigned char*>(p.tickets) - L.tickets_off, dtype, flags, s);
       if (rc > 0 || (rc < 0 && rc != -1000)) return rc;
-    } else {
+    }
+    if (rc == -1000) {
+      // (the developer bits of the flags address the scan kernel unless the round-1 kernel was asked for)
       rc = rtm3d::launch_planes(q, dtype, static_cast<int>((flags >> 8) & 0xFu), (flags & RTM3D_FLAG_NO_SPECULATION) ? 0 : 1,
-                                static_cast<int>((flags >> 16) & 0xFFu), static_cast<int>((flags >> 24) & 0xFu), s);   // -1000: shape not eligible
+                                static_cast<int>((flags >> 16) & 0xFFu), (flags & RTM3D_FLAG_LEGACY_PLANES) ? static_cast<int>((flags >> 24) & 0xFu) : 0, s);   // -1000: shape not eligible
       if (rc != -1000) if (int e = cuda_fail(rc, "decode (plane-streaming kernel) launch")) return e;
     }
     if (rc != -1000) return launch_epilogues(q, dtype, flags, s);
@@ -212,6 +217,26 @@ int rtm3d_decode_main(const void* hm, const void* off, const void* off2, int dty
   p.cls = cls; p.score = score; p.proj = proj; p.verts = verts; p.bbox = bbox; p.flat = flat; p.counts = counts;
   carve(p, L, ws);
   return dispatch(p, L, dtype, rtm3d::kModeMain, flags, static_cast<cudaStream_t>(stream));
+}
+
+int rtm3d_select_main(const void* hm, int dtype, int B, int C, int H, int W, int K, float thresh, float* score, int32_t* flat,
+                      int32_t* counts, void* ws, size_t ws_bytes, unsigned flags, void* stream) {
+  if (!hm || !score || !flat || !counts || !ws) return fail(RTM3D_ERR_NULL, "NULL pointer argument");
+  if (dtype != RTM3D_F32 && dtype != RTM3D_BF16) return fail(RTM3D_ERR_DTYPE, "dtype %d", dtype);
+  if (int e = check_shape(B, C, H, W, K)) return e;
+  if (static_cast<long long>(K) > static_cast<long long>(C) * H * W) return fail(RTM3D_ERR_TOPK, "K=%d > C*H*W", K);
+  if (!(thresh >= 0.0f)) return fail(RTM3D_ERR_THRESH, "score threshold must be >= 0 (got %g)", thresh);
+  if (reinterpret_cast<uintptr_t>(hm) % elem_size(dtype) || reinterpret_cast<uintptr_t>(ws) % 256)
+    return fail(RTM3D_ERR_ALIGN, "misaligned pointer (map: element size, ws: 256 B)");
+  const rtm3d::WorkspaceLayout L = rtm3d::workspace_layout(B, C, H, W, K);
+  if (ws_bytes < L.total) return fail(RTM3D_ERR_WORKSPACE, "workspace %zu B < required %zu B", ws_bytes, L.total);
+  rtm3d::DecodeParams p{};
+  p.hm = hm; p.off = nullptr; p.off2 = nullptr;                  // no regression maps: the selection stops before the gathers
+  p.B = B; p.C = C; p.H = H; p.W = W; p.n_vert = 1; p.K = K;
+  p.thresh = thresh; p.down = 1.f; p.t0 = prefilter_logit(thresh);
+  p.score = score; p.flat = flat; p.counts = counts;
+  carve(p, L, ws);
+  return dispatch(p, L, dtype, rtm3d::kModeMain, flags | RTM3D_FLAG_NO_EPILOGUE, static_cast<cudaStream_t>(stream));
 }
 
 int rtm3d_decode_main_host(const void* hm_host, const void* off_host, const void* off2_host, int dtype, int B, int C,
@@ -341,9 +366,11 @@ int rtm3d_decode_fused(const void* hm, const void* off, const void* off2, const 
       rc = scan_and_select(q, L, ws, dtype, flags, s, one_kernel ? &f : nullptr);
       if (rc > 0 || (rc < 0 && rc != -1000)) return rc;
       if (rc == 0 && (one_kernel || (flags & RTM3D_FLAG_NO_SELECT))) return 0;
-    } else {
+    }
+    if (rc == -1000) {
+      if (flags & RTM3D_FLAG_NO_SELECT) return fail(RTM3D_ERR_SHAPE, "RTM3D_FLAG_NO_SELECT: the shape is not served by the scan kernel");
       rc = rtm3d::launch_planes(q, dtype, static_cast<int>((flags >> 8) & 0xFu), (flags & RTM3D_FLAG_NO_SPECULATION) ? 0 : 1,
-                                static_cast<int>((flags >> 16) & 0xFFu), static_cast<int>((flags >> 24) & 0xFu), s);
+                                static_cast<int>((flags >> 16) & 0xFFu), (flags & RTM3D_FLAG_LEGACY_PLANES) ? static_cast<int>((flags >> 24) & 0xFu) : 0, s);
       if (rc != -1000) if (int e = cuda_fail(rc, "decode (plane-streaming kernel, fused) launch")) return e;
     }
     if (rc != -1000) {
@@ -447,7 +474,13 @@ int rtm3d_select_post(const void* off, const void* off2, const void* voff2, int 
   rtm3d::PostFusedParams f{flat, counts, kflat, kscore, off, off2, voff2, B, C, Cv, H, W, n_vert, K, down,
                            cls, proj, verts, bbox, kxy, kpt_proj, kpt_score, kpt_j, verts_cv};
   rtm3d::SelectPostParams q{reinterpret_cast<const unsigned long long*>(base + L.cand_off), reinterpret_cast<const uint32_t*>(base + L.cand_count_off),
-                            Sp, rtm3d::scan_list_cap(K), thresh, score, flat, counts, kscore, kflat, f};
+                            Sp, rtm3d::scan_list_cap(K), thresh, score, flat, counts, kscore, kflat, f,
+#ifdef RTM3D_DEV
+                            rtm3d::debug_get_stats()
+#else
+                            nullptr
+#endif
+  };
   return cuda_fail(rtm3d::launch_select_post(q, dtype, static_cast<cudaStream_t>(stream)), "select + post kernel launch");
 }
 

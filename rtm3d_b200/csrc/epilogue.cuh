@@ -13,6 +13,17 @@ namespace rtm3d {
 template <typename T>
 static __device__ __noinline__ void block_emit_main(const DecodeParams& p, int b, const uint64_t* sorted, int cnt) {
   const int V = p.n_vert, K = p.K, HW = p.H * p.W;
+  if (p.off == nullptr) {
+    // selection only (rtm3d_select_main): score, flat index and count; the caller's own epilogue follows
+    for (int j = threadIdx.x; j < K; j += blockDim.x) {
+      const size_t row = static_cast<size_t>(b) * K + j;
+      const bool valid = j < cnt;
+      p.score[row] = valid ? key_score(sorted[j]) : 0.f;
+      p.flat[row] = valid ? static_cast<int32_t>(key_flat(sorted[j])) : -1;
+    }
+    if (threadIdx.x == 0) p.counts[b] = cnt;
+    return;
+  }
   int vp = 1;
   while (vp < V) vp <<= 1;                       // lanes per detection (power of two <= 16)
   const int items = K * vp;

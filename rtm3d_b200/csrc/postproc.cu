@@ -1,6 +1,7 @@
 // Post-selection kernels: keypoint grouping (Tier B, models/model.py:134-162) and closed-form 3D recovery (Tier C).
 #include "common.cuh"
 #include "params.h"
+#include "../../include/rtm3d_decode.h"
 #include "postproc.h"
 #include "select_common.cuh"
 #include <cooperative_groups.h>
@@ -289,20 +290,33 @@ template <> __device__ __forceinline__ float gather_ld<__nv_bfloat16>(const __nv
 //   (2) per (detection, channel): vertex regress (models/model.py:63-69) + nearest candidate (:144-161),
 //   (3) per detection: class, centre, 2D box (:70-73) -- as in post_fused_kernel, same arithmetic and association order.
 struct __align__(8) PostDet { int flat; float mx, my; };
+#ifdef RTM3D_DEV
+#define SP_MARK(i) do { if (sp.stats && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); sp.stats[1024 + (static_cast<size_t>(blockIdx.x) * 8 + (i))] = t_; } } while (0)
+#else
+#define SP_MARK(i) do { } while (0)
+#endif
+constexpr int kSpThreads = 128;              // 4 warps: 8 CTAs per SM, the 4 B CTAs of a 256-image batch are resident at once
+constexpr int kSpWarps = kSpThreads / 32;
+
 template <typename T>
-__global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kPostThreads) select_post_kernel(const SelectPostParams sp, int ns) {
+__global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kSpThreads, 8) select_post_kernel(const SelectPostParams sp, int ns, int sort_bytes, int list_slots) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t s_n;
   __shared__ int s_count;
+  __shared__ int s_cnt[kFastLists];
   cg::cluster_group cluster = cg::this_cluster();
   const PostFusedParams& p = sp.post;
-  const int b = blockIdx.x / kPostSplit, rank = static_cast<int>(cluster.block_rank()), tid = threadIdx.x;
+  const int b = blockIdx.x / kPostSplit, rank = static_cast<int>(cluster.block_rank()), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = p.K, Cv = p.Cv, V = p.n_vert, HW = p.H * p.W;
   const int KP = K + 1;                                              // padded row: channels start in different banks
   const int per = (K + kPostSplit - 1) / kPostSplit;                 // detections per CTA
   const int n0 = rank * per, n1 = min(K, n0 + per);
-  uint64_t* s_keys = reinterpret_cast<uint64_t*>(smem_raw);           // [ns] sort buffer (tail: filler scratch)
-  float* s_xy = reinterpret_cast<float*>(s_keys + ns);                // [Cv][KP][2] candidate positions
+  // shared memory: sort area (fast path: [list_slots][kFastPad] sorted lists + [kFastProblems][kFastPad] merged +
+  // [kFastProblems][kFastPad] filler indices; general path: [ns] sort buffer) | candidate positions | vertices | detections
+  uint64_t* s_keys = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* s_top = s_keys + list_slots * kFastPad;
+  uint32_t* s_fill = reinterpret_cast<uint32_t*>(s_top + kFastProblems * kFastPad);
+  float* s_xy = reinterpret_cast<float*>(smem_raw + sort_bytes);      // [Cv][KP][2] candidate positions
   float* s_v = s_xy + static_cast<size_t>(Cv) * KP * 2;              // [per*V*2]  scaled regressed vertices (Tier A)
   PostDet* s_det = reinterpret_cast<PostDet*>(s_v + static_cast<size_t>(per) * V * 2);   // [K] detections: flat index, unscaled centre
   const T* voff2 = reinterpret_cast<const T*>(p.voff2) + static_cast<size_t>(b) * 2 * HW;
@@ -317,21 +331,60 @@ __global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kPostThread
     peer_det[r] = cluster.map_shared_rank(s_det, r);
     peer_count[r] = cluster.map_shared_rank(&s_count, r);
   }
+  SP_MARK(0);
   cluster.sync();          // every CTA of the cluster has started: its shared memory may be written by its peers from here on
-  // ---- (S) selection problems of this CTA
+  SP_MARK(1);
+
+  // ---- (S) the selection problems of this CTA: rank 0 the main problem (C*Sp lists), ranks 1..3 the keypoint planes
+  //      kc = rank-1, rank+2, ... (Sp lists each)
   const int n_kpt_ctas = kPostSplit - 1;
-  if (rank == 0) {
-    const int have = block_select_sorted<kPostThreads>(sp.cand, sp.cand_count, sp.list_cap, b * p.C * sp.Sp, p.C * sp.Sp, K, sp.thresh,
-                                                      s_keys, ns, &s_n);
-    // every listed key has score > thresh (models/model.py:91): the image's count is the number of keys
-    for (int j = tid; j < K; j += kPostThreads) {
+  const int n_prob = rank == 0 ? 1 : (Cv - (rank - 1) + n_kpt_ctas - 1) / n_kpt_ctas;     // (<= 0: nothing to do)
+  const int lists_per_prob = rank == 0 ? p.C * sp.Sp : sp.Sp;
+  const int n_lists = n_prob > 0 ? n_prob * lists_per_prob : 0;
+  auto first_list = [&](int pr) {                                    // first strip of this CTA's pr-th problem
+    return rank == 0 ? b * p.C * sp.Sp : (p.B * p.C + b * Cv + (rank - 1) + pr * n_kpt_ctas) * sp.Sp;
+  };
+  // fast path: every list of the CTA fits the register sort
+  bool fast = K <= kFastPad && n_lists <= list_slots && n_lists <= kFastLists && n_prob <= kFastProblems;
+  {
+    // (lists far beyond the usual ~2 K keys -- ties, plateaus -- go the general way: the register sort takes them in rounds)
+    int too_long = 0;
+    if (fast && tid < n_lists) {
+      const int pr = tid / lists_per_prob;
+      too_long = (sp.cand_count[first_list(pr) + (tid - pr * lists_per_prob)] & ~kCandScoreKeys) > static_cast<uint32_t>(4 * kFastKeys);
+    }
+    fast = fast && !__syncthreads_or(too_long);
+  }
+  if (fast) {
+    // one warp per list: (logit, index) -> (score, index) keys (the sigmoid of models/model.py:85,107 for the listed pixels;
+    // pixels at or below the score floor drop out), register sort, the kFastPad best to shared memory
+    for (int t = warp; t < n_lists; t += kSpWarps) {
+      const int pr = t / lists_per_prob;
+      const int cnt = warp_sort_list(sp.cand, sp.cand_count, sp.list_cap, first_list(pr) + (t - pr * lists_per_prob),
+                                     rank == 0 ? sp.thresh : 0.0f, s_keys + t * kFastPad, lane);
+      if (lane == 0) s_cnt[t] = cnt;
+    }
+    __syncthreads();
+    SP_MARK(2);
+    // problems with several lists: rank-merge (a key's rank = its position in its own list + the larger keys of the others)
+    if (lists_per_prob > 1) {
+      for (int pr = 0; pr < n_prob; ++pr)
+        block_merge_lists<kSpThreads>(s_keys + pr * lists_per_prob * kFastPad, s_cnt + pr * lists_per_prob, lists_per_prob, K, s_top + pr * kFastPad);
+      __syncthreads();
+    }
+  }
+  SP_MARK(3);
+  // Tier A rows of the image from the main problem's K best keys: score, index, count; the detections (index + centre,
+  // models/model.py:48-50) go to all four CTAs
+  auto emit_main = [&](const uint64_t* top, int have) {
+    for (int j = tid; j < K; j += kSpThreads) {
       const size_t row = static_cast<size_t>(b) * K + j;
-      const bool valid = j < have;
-      const int fl = valid ? static_cast<int>(key_flat(s_keys[j])) : -1;
-      sp.score[row] = valid ? key_score(s_keys[j]) : 0.f;
+      const bool valid = j < have;                                   // every listed key has score > thresh (models/model.py:91)
+      const int fl = valid ? static_cast<int>(key_flat(top[j])) : -1;
+      sp.score[row] = valid ? key_score(top[j]) : 0.f;
       sp.flat[row] = fl;
       PostDet dt{fl, 0.f, 0.f};
-      if (valid) {                                                   // centre of the detection (models/model.py:48-50)
+      if (valid) {
         const int rem = fl % HW;
         const int yi = rem / p.W, xi = rem - yi * p.W;
         dt.mx = __fadd_rn(static_cast<float>(xi), sigmoid_ref(gather_ld<T>(off2 + rem)));
@@ -345,51 +398,90 @@ __global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kPostThread
 #pragma unroll
       for (int r = 0; r < kPostSplit; ++r) *peer_count[r] = have;
     }
-  } else {
-    for (int kc = rank - 1; kc < Cv; kc += n_kpt_ctas) {
-      const int plane = p.B * p.C + b * Cv + kc;
-      const int have = block_select_sorted<kPostThreads>(sp.cand, sp.cand_count, sp.list_cap, plane * sp.Sp, sp.Sp, K, 0.0f, s_keys, ns, &s_n);
-      const size_t row0 = (static_cast<size_t>(b) * Cv + kc) * K;
-      // rows have..K-1: 0.0-score fillers = the lowest flat indices that are not among the plane's positive-score peaks (what a
-      // top-K over the zero-filled peak map returns); with fewer than K valid keys the list held ALL peaks
-      uint32_t* fill = reinterpret_cast<uint32_t*>(s_keys + next_pow2(K));       // [K] filler indices, then [2K+8] "taken" flags
-      if (have < K) {
-        const int span = min(K + have, HW);            // the first K-have non-candidate indices lie in [0, K+have)
-        uint32_t* taken = fill + K;
-        for (int i = tid; i < span; i += kPostThreads) {
-          uint32_t t = 0;
-          for (int q = 0; q < have; ++q) t |= (key_flat(s_keys[q]) == static_cast<uint32_t>(i));
-          taken[i] = t;
-        }
-        __syncthreads();
-        if (tid == 0) {
-          int r = have;
-          for (int i = 0; i < span && r < K; ++i)
-            if (!taken[i]) fill[r++] = i;
-        }
-        __syncthreads();
-      }
-      // candidates: score, index, sub-pixel position (models/model.py:113-114, :55-57)
-      for (int j = tid; j < K; j += kPostThreads) {
-        const bool real = j < have;
-        const int fl = static_cast<int>(real ? key_flat(s_keys[j]) : fill[j]);
-        sp.kscore[row0 + j] = real ? key_score(s_keys[j]) : 0.0f;
-        sp.kflat[row0 + j] = fl;
-        const int yi = fl / p.W, xi = fl - yi * p.W;
-        const float x = __fadd_rn(static_cast<float>(xi), sigmoid_ref(gather_ld<T>(voff2 + fl)));
-        const float y = __fadd_rn(static_cast<float>(yi), sigmoid_ref(gather_ld<T>(voff2 + HW + fl)));
+  };
+  // rows have..K-1 of a keypoint plane: 0.0-score fillers = the lowest flat indices that are not among the plane's
+  // positive-score peaks (what a top-K over the zero-filled peak map returns); with fewer than K valid keys the
+  // lists held ALL peaks.  One thread walks the indices in order (rare: fewer than K positive peaks in a whole plane).
+  auto find_fillers = [&](const uint64_t* top, int have, uint32_t* fill) {
+    int r = have;
+    for (int i = 0; i < HW && r < K; ++i) {
+      bool taken = false;
+      for (int q = 0; q < have; ++q) taken |= key_flat(top[q]) == static_cast<uint32_t>(i);
+      if (!taken) fill[r++] = static_cast<uint32_t>(i);
+    }
+  };
+  // one Tier B candidate row: score, index, sub-pixel position (models/model.py:113-114, :55-57), to all four CTAs
+  auto emit_kpt_row = [&](int kc, int j, const uint64_t* top, int have, const uint32_t* fill) {
+    const size_t row = (static_cast<size_t>(b) * Cv + kc) * K + j;
+    const int fl = static_cast<int>(j < have ? key_flat(top[j]) : fill[j]);
+    sp.kscore[row] = j < have ? key_score(top[j]) : 0.0f;
+    sp.kflat[row] = fl;
+    const int yi = fl / p.W, xi = fl - yi * p.W;
+    const float x = __fadd_rn(static_cast<float>(xi), sigmoid_ref(gather_ld<T>(voff2 + fl)));
+    const float y = __fadd_rn(static_cast<float>(yi), sigmoid_ref(gather_ld<T>(voff2 + HW + fl)));
 #pragma unroll
-        for (int r = 0; r < kPostSplit; ++r) peer_xy[r][kc * KP + j] = make_float2(x, y);
-        p.kxy[(row0 + j) * 2] = x; p.kxy[(row0 + j) * 2 + 1] = y;
+    for (int r = 0; r < kPostSplit; ++r) peer_xy[r][kc * KP + j] = make_float2(x, y);
+    p.kxy[row * 2] = x; p.kxy[row * 2 + 1] = y;
+  };
+  if (fast) {
+    auto prob_top = [&](int pr) { return lists_per_prob > 1 ? s_top + pr * kFastPad : s_keys + pr * kFastPad; };
+    auto prob_have = [&](int pr) {
+      int total = 0;
+      for (int o = 0; o < lists_per_prob; ++o) total += s_cnt[pr * lists_per_prob + o];
+      return min(K, total);
+    };
+    if (rank == 0) {
+      emit_main(prob_top(0), prob_have(0));
+    } else {
+      if (tid < n_prob && prob_have(tid) < K) find_fillers(prob_top(tid), prob_have(tid), s_fill + tid * kFastPad);
+      __syncthreads();
+      // every row of every plane of this CTA in one pass: all gathers are in flight together
+      for (int idx = tid; idx < n_prob * K; idx += kSpThreads) {
+        const int pr = idx / K, j = idx - pr * K;
+        emit_kpt_row((rank - 1) + pr * n_kpt_ctas, j, prob_top(pr), prob_have(pr), s_fill + pr * kFastPad);
       }
-      __syncthreads();                                                // the sort buffer is reused by the next plane
+    }
+  } else {
+    for (int pr = 0; pr < n_prob; ++pr) {
+      const int have = block_select_sorted<kSpThreads>(sp.cand, sp.cand_count, sp.list_cap, first_list(pr), lists_per_prob, K,
+                                                       rank == 0 ? sp.thresh : 0.0f, s_keys, ns, &s_n);
+      if (rank == 0) {
+        emit_main(s_keys, have);
+      } else {
+        uint32_t* fill = reinterpret_cast<uint32_t*>(s_keys + next_pow2(K));      // behind the K best keys of the sort buffer
+        if (have < K) {
+          if (tid == 0) find_fillers(s_keys, have, fill);
+          __syncthreads();
+        }
+        for (int j = tid; j < K; j += kSpThreads) emit_kpt_row((rank - 1) + pr * n_kpt_ctas, j, s_keys, have, fill);
+      }
+      __syncthreads();                                                // the sort buffer is reused by the next problem
     }
   }
+  SP_MARK(4);
   cluster.sync();          // every CTA of the image has all candidates and detections (and nobody writes into a peer after this)
+  SP_MARK(5);
   const int n_det = s_count;
   // ---- (2) per (detection, channel): vertex regress (models/model.py:63-69) + nearest candidate (:144-161)
   const int KC = (Cv > V ? Cv : V);                                   // channels that need work per detection
-  for (int w = tid; w < (n1 - n0) * KC; w += kPostThreads) {
+  const int n_items = (n1 - n0) * KC;
+  // the vertex offsets of this thread's first rounds are gathered up front: one DRAM round trip for all of them
+  constexpr int kPre = 2;
+  float pox[kPre], poy[kPre];
+#pragma unroll
+  for (int u = 0; u < kPre; ++u) {
+    const int w = tid + u * kSpThreads;
+    pox[u] = 0.f; poy[u] = 0.f;
+    if (w < n_items) {
+      const int nl = w / KC, k = w - nl * KC, n = n0 + nl;
+      if (n < n_det && k < V) {
+        const int rem = s_det[n].flat % HW;
+        pox[u] = gather_ld<T>(off + static_cast<size_t>(2 * k) * HW + rem);
+        poy[u] = gather_ld<T>(off + static_cast<size_t>(2 * k + 1) * HW + rem);
+      }
+    }
+  }
+  for (int w = tid, u = 0; w < n_items; w += kSpThreads, ++u) {
     const int nl = w / KC, k = w - nl * KC, n = n0 + nl;
     const bool valid = n < n_det;
     float ox = 0.f, oy = 0.f, mx = 0.f, my = 0.f;
@@ -398,8 +490,12 @@ __global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kPostThread
       const int rem = dt.flat % HW;
       mx = dt.mx; my = dt.my;
       if (k < V) {
-        ox = gather_ld<T>(off + static_cast<size_t>(2 * k) * HW + rem);
-        oy = gather_ld<T>(off + static_cast<size_t>(2 * k + 1) * HW + rem);
+        if (u < kPre) {
+          ox = u == 0 ? pox[0] : pox[1]; oy = u == 0 ? poy[0] : poy[1];
+        } else {
+          ox = gather_ld<T>(off + static_cast<size_t>(2 * k) * HW + rem);
+          oy = gather_ld<T>(off + static_cast<size_t>(2 * k + 1) * HW + rem);
+        }
       }
     }
     const float vx = valid ? __fmul_rn(p.down, __fadd_rn(ox, mx)) : 0.f;
@@ -457,8 +553,9 @@ __global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kPostThread
     }
   }
   __syncthreads();
+  SP_MARK(6);
   // ---- (3) per detection: class, centre, 2D box over the regressed vertices (models/model.py:70-73)
-  for (int n = n0 + tid; n < n1; n += kPostThreads) {
+  for (int n = n0 + tid; n < n1; n += kSpThreads) {
     const size_t row = static_cast<size_t>(b) * K + n;
     const int nl = n - n0;
     const bool valid = n < n_det;
@@ -478,22 +575,36 @@ __global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kPostThread
     p.proj[row * 2 + 1] = valid ? __fmul_rn(p.down, s_det[n].my) : 0.f;
     p.bbox[row * 4 + 0] = lo_x; p.bbox[row * 4 + 1] = lo_y; p.bbox[row * 4 + 2] = hi_x; p.bbox[row * 4 + 3] = hi_y;
   }
+  SP_MARK(7);
 }
 
 static int select_post_ns(int K) {
   int ns = 4 * next_pow2(K);
   return ns < 1024 ? 1024 : ns;
 }
-size_t select_post_smem(int Cv, int K, int n_vert) {
+static int select_post_list_slots(int C, int Cv, int Sp) {
+  const int kpt = ((Cv + kPostSplit - 2) / (kPostSplit - 1)) * Sp, main = C * Sp;
+  const int need = kpt > main ? kpt : main;
+  return need > kFastLists ? kFastLists : need;
+}
+static size_t select_post_sort_bytes(int C, int Cv, int Sp, int K) {
+  const size_t fast = static_cast<size_t>(select_post_list_slots(C, Cv, Sp) + kFastProblems) * kFastPad * 8 + static_cast<size_t>(kFastProblems) * kFastPad * 4;
+  const size_t general = static_cast<size_t>(select_post_ns(K)) * 8;
+  return fast > general ? fast : general;
+}
+static size_t select_post_smem_sp(int C, int Cv, int Sp, int K, int n_vert) {
   const size_t per = static_cast<size_t>((K + kPostSplit - 1) / kPostSplit);
-  return static_cast<size_t>(select_post_ns(K)) * 8 + (static_cast<size_t>(Cv) * (K + 1) * 2 + per * n_vert * 2) * sizeof(float) +
+  return select_post_sort_bytes(C, Cv, Sp, K) + (static_cast<size_t>(Cv) * (K + 1) * 2 + per * n_vert * 2) * sizeof(float) +
          static_cast<size_t>(K) * sizeof(PostDet) + 16;
 }
+size_t select_post_smem(int Cv, int K, int n_vert) { return select_post_smem_sp(kFastLists, Cv, 1, K, n_vert); }   // upper bound
 
 int launch_select_post(const SelectPostParams& p, int dtype, cudaStream_t s) {
-  const size_t smem = select_post_smem(p.post.Cv, p.post.K, p.post.n_vert);
+  const size_t smem = select_post_smem_sp(p.post.C, p.post.Cv, p.Sp, p.post.K, p.post.n_vert);
   const unsigned grid = static_cast<unsigned>(p.post.B) * kPostSplit;
   const int ns = select_post_ns(p.post.K);
+  const int sort_bytes = static_cast<int>(select_post_sort_bytes(p.post.C, p.post.Cv, p.Sp, p.post.K));
+  const int list_slots = select_post_list_slots(p.post.C, p.post.Cv, p.Sp);
   static bool attr_set[64][2] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -504,8 +615,8 @@ int launch_select_post(const SelectPostParams& p, int dtype, cudaStream_t s) {
     if (e != cudaSuccess) return static_cast<int>(e);
     if (dev >= 0 && dev < 64) attr_set[dev][di] = true;
   }
-  if (dtype == 0) select_post_kernel<float><<<grid, kPostThreads, smem, s>>>(p, ns);
-  else select_post_kernel<__nv_bfloat16><<<grid, kPostThreads, smem, s>>>(p, ns);
+  if (dtype == 0) select_post_kernel<float><<<grid, kSpThreads, smem, s>>>(p, ns, sort_bytes, list_slots);
+  else select_post_kernel<__nv_bfloat16><<<grid, kSpThreads, smem, s>>>(p, ns, sort_bytes, list_slots);
   return static_cast<int>(cudaGetLastError());
 }
 

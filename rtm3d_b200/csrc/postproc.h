@@ -55,6 +55,7 @@ struct SelectPostParams {
   float thresh;
   float* score; int32_t* flat; int32_t* counts; float* kscore; int32_t* kflat;     // the selection (written here)
   PostFusedParams post;                                                             // maps, shapes, outputs of the epilogues
+  unsigned long long* stats;                                                        // developer timestamps (nullable)
 };
 size_t select_post_smem(int Cv, int K, int n_vert);
 int launch_select_post(const SelectPostParams& p, int dtype, cudaStream_t s);

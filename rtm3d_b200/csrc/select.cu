@@ -9,7 +9,7 @@
 
 namespace rtm3d {
 
-constexpr int kSelThreads = 256;
+constexpr int kSelThreads = 128;
 
 // Tier B rows cnt..K-1: the lowest flat indices that are not among the plane's positive-score peaks (what a top-K over the
 // zero-filled peak map returns).  One warp; scratch >= 3K+8 words.
@@ -46,28 +46,54 @@ static __device__ __noinline__ void warp_fill_kpt(const SelectParams& p, size_t 
 __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p, int ns) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t s_n;
-  const int K = p.K, tid = threadIdx.x;
-  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);                  // [ns] sort buffer
-  uint32_t* scratch = reinterpret_cast<uint32_t*>(keys + ns);              // [3K+8]
+  __shared__ int s_cnt[kFastLists];
+  const int K = p.K, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);                  // [ns] sort buffer | fast path: [n_lists + 1][kFastPad]
   const int n_main = p.C > 0 ? p.B : 0;
   const int q = blockIdx.x;
   const bool is_main = q < n_main;
   const int first = is_main ? q * p.C * p.Sp : (p.B * p.C + (q - n_main)) * p.Sp;
   const int n_lists = is_main ? p.C * p.Sp : p.Sp;
   // strict `score > thresh` of models/model.py:91; 0.0 for the keypoint planes: zero-score pixels are fillers, not peaks
-  const int have = block_select_sorted<kSelThreads>(p.cand, p.cand_count, p.list_cap, first, n_lists, K, is_main ? p.thresh : 0.0f, keys, ns, &s_n);
+  const float lim = is_main ? p.thresh : 0.0f;
+  const uint64_t* top = keys;
+  int have;
+  bool fast = K <= kFastPad && n_lists <= kFastLists && (n_lists + 1) * kFastPad <= ns;
+  {
+    int too_long = 0;
+    if (fast && tid < n_lists) too_long = (p.cand_count[first + tid] & ~kCandScoreKeys) > static_cast<uint32_t>(4 * kFastKeys);
+    fast = fast && !__syncthreads_or(too_long);
+  }
+  if (fast) {
+    // one warp per list (register sort), then the rank-merge of the problem's lists
+    for (int t = warp; t < n_lists; t += kSelThreads / 32) {
+      const int cnt = warp_sort_list(p.cand, p.cand_count, p.list_cap, first + t, lim, keys + t * kFastPad, lane);
+      if (lane == 0) s_cnt[t] = cnt;
+    }
+    __syncthreads();
+    int total = 0;
+    for (int o = 0; o < n_lists; ++o) total += s_cnt[o];
+    have = min(K, total);
+    if (n_lists > 1) {
+      block_merge_lists<kSelThreads>(keys, s_cnt, n_lists, K, keys + n_lists * kFastPad);
+      __syncthreads();
+      top = keys + n_lists * kFastPad;
+    }
+  } else {
+    have = block_select_sorted<kSelThreads>(p.cand, p.cand_count, p.list_cap, first, n_lists, K, lim, keys, ns, &s_n);
+  }
   if (is_main) {
     // every key of a main list has score > thresh: counts = number of keys
     const int b = q;
     for (int j = tid; j < K; j += kSelThreads) {
       const size_t row = static_cast<size_t>(b) * K + j;
       const bool valid = j < have;
-      p.score[row] = valid ? key_score(keys[j]) : 0.f;
-      p.flat[row] = valid ? static_cast<int32_t>(key_flat(keys[j])) : -1;
+      p.score[row] = valid ? key_score(top[j]) : 0.f;
+      p.flat[row] = valid ? static_cast<int32_t>(key_flat(top[j])) : -1;
     }
     if (tid == 0) p.counts[b] = have;
   } else if (tid < 32) {
-    warp_fill_kpt(p, static_cast<size_t>(q - n_main) * K, keys, have, scratch, tid);
+    warp_fill_kpt(p, static_cast<size_t>(q - n_main) * K, top, have, reinterpret_cast<uint32_t*>(keys + ns), tid);
   }
 }
 

@@ -89,4 +89,115 @@ __device__ __forceinline__ int block_select_sorted(const unsigned long long* can
   return have;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fast path: one warp sorts one list in registers, the lists of a problem are rank-merged.
+constexpr int kFastKeys = 256;               // keys of one list a round of the register sort takes (8 per lane)
+constexpr int kFastPad = 128;                // sorted keys kept per list (>= K on the fast path)
+constexpr int kFastLists = 16;               // lists per CTA on the fast path
+constexpr int kFastProblems = 4;             // selection problems per CTA on the fast path
+
+// Descending bitonic sort of 256 keys held 8 per lane (network element e = lane * 8 + k) in registers: partner distances below
+// 8 are exchanges inside a lane, the others one 64-bit shuffle per key.
+__device__ __forceinline__ void warp_sort256_desc(unsigned long long (&x)[8], int lane) {
+#pragma unroll
+  for (int kk = 2; kk <= 256; kk <<= 1) {
+#pragma unroll
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      if (j >= 8) {
+        const int lj = j >> 3;                                   // partner lane distance
+        const bool lower = (lane & lj) == 0;
+        const bool desc = (lane & (kk >> 3)) == 0;               // (e & kk) == 0  (kk = 256: always)
+        const bool take_max = lower == desc;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const unsigned long long o = __shfl_xor_sync(0xffffffffu, x[k], lj);
+          const bool gt = x[k] > o;
+          x[k] = (gt == take_max) ? x[k] : o;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if ((k & j) == 0) {
+            const int q = k | j;
+            const bool desc = (kk < 8) ? ((k & kk) == 0) : ((lane & (kk >> 3)) == 0);
+            const unsigned long long a = x[k], c = x[q];
+            const bool keep = (a > c) == desc;                    // a stays in front
+            x[k] = keep ? a : c;
+            x[q] = keep ? c : a;
+          }
+        }
+      }
+    }
+  }
+}
+
+// number of keys of the descending list r[0..len) that are larger than `key`
+__device__ __forceinline__ int count_greater_u64(const uint64_t* r, int len, uint64_t key) {
+  int lo = 0, hi = len;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (r[mid] > key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// One warp: the kFastPad best (score, index) keys of candidate list `strip`, sorted, into dst[0..kFastPad) (zeros behind the
+// valid ones); returns min(valid, kFastPad).  (logit, index) keys become (score, index) keys here -- the sigmoid of
+// models/model.py:85,107 for the listed pixels -- and pixels at or below the score floor `lim` drop out.  The first round
+// takes 256 keys; a longer list goes on in rounds of 128 new keys merged with the 128 best so far.
+__device__ __forceinline__ int warp_sort_list(const unsigned long long* cand, const uint32_t* cand_count, int list_cap, int strip, float lim,
+                                              uint64_t* dst, int lane) {
+  const uint32_t raw = cand_count[strip];
+  const int cnt = static_cast<int>(raw & ~kCandScoreKeys);
+  const bool score_keys = (raw & kCandScoreKeys) != 0u;
+  const unsigned long long* src = cand + static_cast<size_t>(strip) * list_cap;
+  int valid = 0;
+  for (int base = 0; base == 0 || base < cnt; base += (base == 0 ? kFastKeys : kFastPad)) {
+    unsigned long long x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      unsigned long long key = 0ull;
+      if (base != 0 && k < 4) {
+        key = dst[k * 32 + lane];                                // the best so far (any order)
+      } else {
+        const int i = base + (base == 0 ? k : k - 4) * 32 + lane;
+        if (i < cnt) {
+          key = src[i];
+          if (!score_keys) {
+            const float sc = sigmoid_ref(f32_unord(static_cast<uint32_t>(key >> 32)));
+            key = sc > lim ? make_key(sc, key_flat(key)) : 0ull;
+          }
+        }
+        valid += key != 0ull ? 1 : 0;
+      }
+      x[k] = key;
+    }
+    warp_sort256_desc(x, lane);
+    __syncwarp();
+    if (lane < kFastPad / 8) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dst[lane * 8 + k] = x[k];
+    }
+    __syncwarp();
+  }
+  valid = __reduce_add_sync(0xffffffffu, valid);
+  return min(valid, kFastPad);
+}
+
+// Rank-merge of `nl` sorted lists (lists[l * kFastPad ..], cnt[l] valid keys each) into top[0..K): a key's rank = its
+// position in its own list + the number of larger keys in the others (keys are distinct).  All NT threads; the caller
+// synchronises afterwards.
+template <int NT>
+__device__ __forceinline__ void block_merge_lists(const uint64_t* lists, const int* cnt, int nl, int K, uint64_t* top) {
+  for (int idx = threadIdx.x; idx < nl * kFastPad; idx += NT) {
+    const int li = idx / kFastPad, pos = idx - li * kFastPad;
+    if (pos >= cnt[li]) continue;
+    const uint64_t key = lists[li * kFastPad + pos];
+    int rk = pos;
+    for (int o = 0; o < nl; ++o)
+      if (o != li) rk += count_greater_u64(lists + o * kFastPad, cnt[o], key);
+    if (rk < K) top[rk] = key;
+  }
+}
+
 }  // namespace rtm3d

@@ -189,6 +189,29 @@ class HeatmapDecoder:
         _native.check(rc, "rtm3d_decode_main")
         return out
 
+    def select_main(self, main: torch.Tensor) -> PackedDetections:
+        """Selection only (models/model.py:77-98 without the gathers): ``score``, ``flat`` and ``counts`` of the K best peaks
+        per image; the other fields of the returned PackedDetections are None.  For epilogues of the caller's own behind the
+        peaks -- ``decode_box3d`` (BASELINE configs[2])."""
+        _check_map(main, "main_kf")
+        B, C, H, W = main.shape
+        dev, K = main.device, self.topk
+        with torch.cuda.device(dev):
+            ws, stream = self._workspace(dev, B, C, H, W)
+            okey = ("select", dev.index, B, K)
+            out = self._out.get(okey) if self.reuse_outputs else None
+            if out is None:
+                out = PackedDetections(cls=None, score=torch.empty((B, K), dtype=torch.float32, device=dev), proj=None, verts=None,
+                                       bbox=None, flat=torch.empty((B, K), dtype=torch.int32, device=dev),
+                                       counts=torch.empty((B,), dtype=torch.int32, device=dev))
+                if self.reuse_outputs:
+                    self._out[okey] = out
+            rc = self._lib.rtm3d_select_main(main.data_ptr(), _dtype_code(main), B, C, H, W, K, self.score_thresh,
+                                             out.score.data_ptr(), out.flat.data_ptr(), out.counts.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), self.flags, stream)
+        _native.check(rc, "rtm3d_select_main")
+        return out
+
     def decode(self, pred_logits: Sequence[torch.Tensor]):
         """Drop-in for ``Model.inference`` (models/model.py:29-75)."""
         p = self.decode_packed(pred_logits)
@@ -318,6 +341,16 @@ class HeatmapDecoder:
                 det.flat.data_ptr(), det.counts.data_ptr(), cand.score.data_ptr(), cand.xy.data_ptr(), cand.flat.data_ptr(),
                 grp.kpt_proj.data_ptr(), grp.kpt_score.data_ptr(), grp.kpt_j.data_ptr(), grp.verts.data_ptr(),
                 ws.data_ptr(), ws.numel(), self.flags | stage_flags, stream)
+            if marks is not None and not legacy and rc == _native.ERR_SHAPE:
+                # the scan kernel does not serve this shape (planes larger than its ring): the round-1 kernels in two stages
+                legacy = True
+                rc = self._lib.rtm3d_decode_fused(
+                    main.data_ptr(), off.data_ptr(), off2.data_ptr(), kpt_logits.data_ptr(), voff2.data_ptr(), dt,
+                    B, C, Cv, H, W, V, K, self.score_thresh, self.down_sample,
+                    det.cls.data_ptr(), det.score.data_ptr(), det.proj.data_ptr(), det.verts.data_ptr(), det.bbox.data_ptr(),
+                    det.flat.data_ptr(), det.counts.data_ptr(), cand.score.data_ptr(), cand.xy.data_ptr(), cand.flat.data_ptr(),
+                    grp.kpt_proj.data_ptr(), grp.kpt_score.data_ptr(), grp.kpt_j.data_ptr(), grp.verts.data_ptr(),
+                    ws.data_ptr(), ws.numel(), self.flags | _native.FLAG_NO_GROUP | _native.FLAG_NO_EPILOGUE, stream)
             mark()
             _native.check(rc, "rtm3d_decode_fused")
             if marks is not None and legacy:
@@ -342,8 +375,9 @@ class HeatmapDecoder:
     # ------------------------------------------------------------------ Tier C
     def decode_box3d(self, det: PackedDetections, reg: torch.Tensor, cam: torch.Tensor, dim_ref: torch.Tensor,
                      n_classes: int, multibin: bool = False, sigmoid_subpixel: bool = False,
-                     depth_ref=(28.01, 16.32)):
-        """Closed-form 3D recovery at the Tier A peaks (NOT in the reference; spec: oracle/box3d_ref.py)."""
+                     depth_ref=(28.01, 16.32), cached: bool = False):
+        """Closed-form 3D recovery at the Tier A peaks (NOT in the reference; spec: oracle/box3d_ref.py).  ``cached``: reuse the
+        result buffers of the previous call with the same shapes (valid until the next call)."""
         _check_map(reg, "regression map")
         B, Creg, H, W = reg.shape
         K = det.score.shape[1]
@@ -352,11 +386,16 @@ class HeatmapDecoder:
         dim_ref = dim_ref.to(device=dev, dtype=torch.float32).contiguous().view(n_classes, 3)
         mode = (1 if multibin else 0) | (2 if sigmoid_subpixel else 0)
         with torch.cuda.device(dev):
-            out = dict(loc=torch.empty((B, K, 3), dtype=torch.float32, device=dev),
-                       dim=torch.empty((B, K, 3), dtype=torch.float32, device=dev),
-                       alpha=torch.empty((B, K), dtype=torch.float32, device=dev),
-                       rot_y=torch.empty((B, K), dtype=torch.float32, device=dev),
-                       corners2d=torch.empty((B, K, 8, 2), dtype=torch.float32, device=dev))
+            okey = ("box3d", dev.index, B, K)
+            out = self._out.get(okey) if cached else None
+            if out is None:
+                out = dict(loc=torch.empty((B, K, 3), dtype=torch.float32, device=dev),
+                           dim=torch.empty((B, K, 3), dtype=torch.float32, device=dev),
+                           alpha=torch.empty((B, K), dtype=torch.float32, device=dev),
+                           rot_y=torch.empty((B, K), dtype=torch.float32, device=dev),
+                           corners2d=torch.empty((B, K, 8, 2), dtype=torch.float32, device=dev))
+                if cached:
+                    self._out[okey] = out
             rc = self._lib.rtm3d_decode_box3d(det.flat.data_ptr(), det.counts.data_ptr(), reg.data_ptr(), _dtype_code(reg),
                                               B, n_classes, H, W, Creg, K, mode, cam.data_ptr(), dim_ref.data_ptr(),
                                               float(depth_ref[0]), float(depth_ref[1]), out["loc"].data_ptr(),
