@@ -76,7 +76,9 @@ struct StripDesc {       // written by the producer, read by the scan warps
 };
 
 struct __align__(16) ScanCtl {
-  unsigned long long full[kMaxSlots];     // producer -> scan warps: chunk landed
+  unsigned long long full_a[kMaxSlots];   // producer -> scan warps, per strip in flight (queue entry): the chunks that hold the first
+                                          // kSelRegs register rows have landed ...
+  unsigned long long full_b[kMaxSlots];   // ... the rest of the strip has landed
   unsigned long long empty[kMaxSlots];    // scan warps -> producer: slot free
   StripDesc queue[kMaxSlots];             // the producer is never more than S strips ahead
   float t_warp[kScanWarps];
@@ -247,8 +249,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_planes_kernel(const Scan
   unsigned char* ring = smem;
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) {
-      pl::mbar_init(pl::smem_u32(&ctl.full[s]), 1);
+    for (int s = 0; s < kMaxSlots; ++s) {
+      pl::mbar_init(pl::smem_u32(&ctl.full_a[s]), 1);
+      pl::mbar_init(pl::smem_u32(&ctl.full_b[s]), 1);
       pl::mbar_init(pl::smem_u32(&ctl.empty[s]), 1);
     }
     ctl.n_list[0] = 0u; ctl.n_list[1] = 0u;
@@ -304,6 +307,16 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_planes_kernel(const Scan
         } else {
           d.n_chunks = 0; d.top_halo = 0; d.rows = 0; d.y0 = 0; d.flat_base = 0u; d.is_main = 0;
         }
+        // two barriers per strip: the scan warps wait once for the part the first threshold is computed from and once for
+        // the rest, not once per chunk
+        const uint32_t q = seq & (kMaxSlots - 1);
+        const uint32_t bar_a = pl::smem_u32(&ctl.full_a[q]), bar_b = pl::smem_u32(&ctl.full_b[q]);
+        int chunks_a = 0;
+        if (!end) {
+          const uint32_t halo_bytes = static_cast<uint32_t>(d.top_halo) * g.row_bytes;
+          const uint32_t bytes_sel = halo_bytes + static_cast<uint32_t>(min(kSelRegs * kScanConsumers, d.rows * g.gpr)) * 16u;
+          chunks_a = min(d.n_chunks, static_cast<int>(__umulhi(bytes_sel + g.slot_bytes - 1u, g.slot_bytes_magic)));
+        }
         const int nch = end ? 1 : d.n_chunks;
         for (int c = 0; c < nch; ++c) {
           if (issued >= static_cast<uint32_t>(S)) {
@@ -311,15 +324,22 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_planes_kernel(const Scan
             pl::mbar_wait(pl::smem_u32(&ctl.empty[slot]), par ^ 1u, p.status, 0xE2000001u, 32);
             pw += SCAN_CLK() - w0;
           }
-          if (c == 0) ctl.queue[seq & (kMaxSlots - 1)] = d;       // (made visible to the scan warps by the barrier operation below)
-          const uint32_t bar = pl::smem_u32(&ctl.full[slot]);
-          if (end) {
-            pl::mbar_arrive(bar);
-          } else {
+          if (c == 0) {
+            ctl.queue[q] = d;                                      // (made visible to the scan warps by the barrier operation below)
+            if (end) {
+              pl::mbar_arrive(bar_a);
+            } else {
+              const uint32_t total = static_cast<uint32_t>(n_loaded) * g.row_bytes;
+              const uint32_t bytes_a = min(static_cast<uint32_t>(chunks_a) * g.slot_bytes, total);
+              pl::mbar_arrive_expect_tx(bar_a, bytes_a);
+              if (total > bytes_a) pl::mbar_arrive_expect_tx(bar_b, total - bytes_a); else pl::mbar_arrive(bar_b);
+            }
+          }
+          if (!end) {
             const int r0 = c * g.slot_rows;
             const uint32_t bytes = static_cast<uint32_t>(min(g.slot_rows, n_loaded - r0)) * g.row_bytes;
-            pl::mbar_arrive_expect_tx(bar, bytes);
-            pl::bulk_g2s(pl::smem_u32(ring + static_cast<size_t>(slot) * g.slot_bytes), src + static_cast<size_t>(r0) * g.row_bytes, bytes, bar, policy);
+            pl::bulk_g2s(pl::smem_u32(ring + static_cast<size_t>(slot) * g.slot_bytes), src + static_cast<size_t>(r0) * g.row_bytes, bytes,
+                         c < chunks_a ? bar_a : bar_b, policy);
           }
           ++issued;
           if (++slot == static_cast<uint32_t>(S)) { slot = 0; par ^= 1u; }
@@ -337,7 +357,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_planes_kernel(const Scan
     }
   } else {
     // ================================ scan warps ================================
-    uint32_t slot = 0, par = 0, seq = 0;
+    uint32_t seq = 0;
     const uint32_t lt = (1u << lane) - 1u;
     unsigned short* wl = ctl.wl[warp];
     long long st_deepen = 0, st_exact = 0, st_keys = 0, st_strips = 0;
@@ -348,11 +368,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_planes_kernel(const Scan
     const int lane_g = warp * 32 + lane;
     while (true) {
       const long long c0 = SCAN_CLK();
-      pl::mbar_wait(pl::smem_u32(&ctl.full[slot]), par, p.status, 0xE2000002u, 32);
+      const uint32_t q = seq & (kMaxSlots - 1), qpar = (seq / kMaxSlots) & 1u;
+      pl::mbar_wait(pl::smem_u32(&ctl.full_a[q]), qpar, p.status, 0xE2000002u, 32);
       const long long c1 = SCAN_CLK();
-      const StripDesc d = ctl.queue[seq & (kMaxSlots - 1)];
+      const StripDesc d = ctl.queue[q];
       if (d.strip < 0) break;
-      if (++slot == static_cast<uint32_t>(S)) { slot = 0; par ^= 1u; }
       const int buf = static_cast<int>(seq & 1u);
       uint32_t* n_list = &ctl.n_list[buf];
       uint32_t* n_strict = &ctl.n_strict[buf];
@@ -375,17 +395,6 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_planes_kernel(const Scan
         if (lane_off >= view.ring_bytes) lane_off -= view.ring_bytes;
         const int n_full = G / kScanConsumers;
         const int n_mine = n_full + ((lane_g < G - n_full * kScanConsumers) ? 1 : 0);           // register rows in which this thread has a group
-        // chunks that hold the first kSelRegs register rows
-        const uint32_t bytes_a = halo_bytes + static_cast<uint32_t>(min(kSelRegs * kScanConsumers, G)) * 16u;
-        const int chunks_a = min(d.n_chunks, static_cast<int>(__umulhi(bytes_a + g.slot_bytes - 1u, g.slot_bytes_magic)));
-        int landed = 1;
-        auto wait_chunks = [&](int want) {
-          while (landed < want) {
-            pl::mbar_wait(pl::smem_u32(&ctl.full[slot]), par, p.status, 0xE2000003u, 32);
-            if (++slot == static_cast<uint32_t>(S)) { slot = 0; par ^= 1u; }
-            ++landed;
-          }
-        };
         auto load_reg = [&](int r) {
           // (branch-free: a register row without a group of this thread re-reads the thread's first group)
           const bool mine = r < n_mine;
@@ -398,7 +407,6 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_planes_kernel(const Scan
           for (int i = 1; i < E; ++i) mx = fmaxf(mx, v[i]);
           return mine ? mx : -INFINITY;
         };
-        wait_chunks(chunks_a);
 #pragma unroll
         for (int r = 0; r < kSelRegs; ++r) m[r] = load_reg(r);
         if (g.rank_j > 0) {
@@ -419,7 +427,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_planes_kernel(const Scan
           const uint32_t tmin = __reduce_min_sync(0xffffffffu, ctl.t_sub[min(lane, kScanWarps - 1)]);
           tw = tmin < 0x00800000u ? -INFINITY : f32_unord(tmin);
         }
-        wait_chunks(d.n_chunks);
+        pl::mbar_wait(pl::smem_u32(&ctl.full_b[q]), qpar, p.status, 0xE2000003u, 32);
 #pragma unroll
         for (int r = kSelRegs; r < kGroupRegs; ++r) m[r] = load_reg(r);
       }

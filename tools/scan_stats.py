@@ -10,7 +10,7 @@ wl = sys.argv[1] if len(sys.argv) > 1 else "cfg4"
 dtype = "bf16" if "bf16" in sys.argv else "f32"
 w = bench.WORKLOADS[wl]
 dev = torch.device("cuda:0")
-logits, kpt = bench.make_inputs(torch, w, dev, 1234, dtype=dtype)
+logits, kpt, _ = bench.make_inputs(torch, w, dev, 1234, dtype=dtype)
 dbg = int(os.environ.get("SCAN_DEBUG", "0"))
 dec = HeatmapDecoder(0.4, w["K"], 4.0, reuse_outputs=True, debug=dbg)
 lib = _native.lib()
