@@ -242,7 +242,7 @@ def run_b200(args, w_job):
                                   "Model.inference (incl. the clone of models/model.py:27 and the keypoint branch)"}
 
     import torch.distributed as dist
-    from rtm3d_b200 import HeatmapDecoder, HostDecodeSession
+    from rtm3d_b200 import HeatmapDecoder, HostDecodeSession, _native
     from rtm3d_b200.decoder import PackedDetections
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -252,17 +252,52 @@ def run_b200(args, w_job):
         sys.stdout.flush()
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
+        # the gather's NCCL kernel shares the GPU with the next batch's decode: keep it to the few SMs the scan kernel leaves
+        # free (--max-ctas), unless the environment says otherwise
+        if args.nccl_ctas > 0:
+            os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_ctas))
+            os.environ.setdefault("NCCL_MIN_CTAS", "1")
         dist.init_process_group("nccl", device_id=dev)
 
     K, Cv = w["K"], w["kpt"]
-    # N > 1: the all-gather's NCCL kernel runs beside the next batch's decode; the persistent scan kernel leaves it a few
-    # SMs instead of queueing its last CTAs behind it (--max-ctas; 0 = one CTA per SM)
-    max_ctas = args.max_ctas if args.max_ctas >= 0 else (0 if world == 1 else 144)
+
+    def setup_gather():
+        """Gather buffers of the two result slots.  Preferred: symmetric memory (every rank's buffer mapped into every process)
+        -- the select + post kernel then stores the wire rows straight into all ranks' buffers (rtm3d_decode_fused_gather) and
+        the only other cross-GPU operation of a step is a barrier on the gather stream.  Else: rtm3d_pack_wire + NCCL all-gather."""
+        per = K * PackedDetections.WORDS + 1
+        go = dict(stream=torch.cuda.Stream(device=dev), gathered=[None, None], mode="nccl", peers=[None, None], hdl=None)
+        if args.gather == "p2p" and Cv and not w.get("reg"):
+            try:
+                import ctypes
+                import torch.distributed._symmetric_memory as symm_mem
+                slot_words = world * B * per + world           # rows of every rank + one arrival flag per source rank
+                buf = symm_mem.empty((2, slot_words), dtype=torch.int32, device=dev)
+                hdl = symm_mem.rendezvous(buf, dist.group.WORLD.group_name)
+                for slot in range(2):
+                    go["peers"][slot] = (ctypes.c_void_p * world)(*[int(ptr) + slot * slot_words * 4 for ptr in hdl.buffer_ptrs])
+                buf.zero_()
+                go.update(mode="p2p", hdl=hdl, buf=buf, full=[buf[s_][:world * B * per].view(world * B, per) for s_ in range(2)],
+                          mine=[None, None], step_id=0)
+                torch.cuda.synchronize()
+                dist.barrier()
+                return go
+            except Exception as e:
+                print(f"bench.py: symmetric-memory gather not available ({e!r}); NCCL all-gather", file=sys.stderr)
+        go["full"] = [torch.empty((world * B, per), dtype=torch.int32, device=dev) for _ in range(2)]
+        go["mine"] = [torch.empty((B, per), dtype=torch.int32, device=dev) for _ in range(2)]
+        return go
+
+    gather_out = setup_gather() if world > 1 else None
+    # N > 1 with the NCCL all-gather: its kernel runs beside the next batch's decode; the persistent scan kernel leaves it a
+    # few SMs instead of queueing its last CTAs behind it (--max-ctas; 0 = one CTA per SM).  The fused peer-to-peer gather
+    # has no second kernel to make room for.
+    max_ctas = args.max_ctas if args.max_ctas >= 0 else (0 if (world == 1 or gather_out["mode"] == "p2p") else 144)
     # result buffers are reused from call to call (saves ~35 us of host time per step); at N > 1 two decoders alternate so
     # that a batch's results stay untouched while the gather stream packs them
     mk_dec = lambda: HeatmapDecoder(THRESH, K, DOWN, max_ctas=max_ctas, reuse_outputs=True)
     decs_dev = [mk_dec() for _ in range(1 if world == 1 else 2)]
-    nsets = 2
+    nsets = 2                                 # (== the two result slots: step i uses input set, decoder and slot i & 1)
     sets = [make_inputs(torch, w, dev, 1234 + rank + 100 * s, dtype=args.dtype) for s in range(nsets)]
     elem = 2 if args.dtype == "bf16" else 4
     heat_bytes = B * (w["C"] + Cv) * w["H"] * w["W"] * elem
@@ -273,11 +308,11 @@ def run_b200(args, w_job):
     else:
         names = ["scan+select+epilogue(main)"]
     launches_per_step = {"scan_planes(main+kpt)": 1, "select_post": 1, "scan+select(main)": 2, "box3d": 1, "scan+select+epilogue(main)": 3}
-    n_launches = sum(launches_per_step[n] for n in names) + (1 if world > 1 else 0)    # + the wire-packing kernel of the gather
+    n_launches = sum(launches_per_step[n] for n in names)       # (+ the wire-packing kernel when the gather goes through NCCL: added below)
 
-    gather_out = None
+    capturing = False
 
-    def decode(i, dec, inputs, marks=None):
+    def decode(i, dec, inputs, marks=None, gather=None):
         logits, kpt, box = inputs
 
         def mark():
@@ -293,38 +328,48 @@ def run_b200(args, w_job):
             mark()
             return det
         if Cv:
-            det, _, _ = dec.decode_with_keypoints(logits, kpt, marks=marks)
+            det, _, _ = dec.decode_with_keypoints(logits, kpt, marks=marks, gather=gather)
             return det
         mark()
         det = dec.decode_packed(logits)
         mark()
         return det
 
-    def step(i, marks=None, inputs=None):
-        nonlocal gather_out
-        dec = decs_dev[i % len(decs_dev)]
-        if world > 1 and gather_out is not None and gather_out["packed"][i & 1] is not None:
-            torch.cuda.current_stream().wait_event(gather_out["packed"][i & 1])      # batch i-2's results have been packed
-        det = decode(i, dec, inputs if inputs is not None else sets[i % nsets], marks)
-        if world > 1:
-            # the path's one collective: pack (one launch of the library) + all-gather of the fixed-size
-            # detections.  It runs on a second stream behind an event, so the gather of batch i overlaps the decode of
-            # batch i+1; the timed region ends with a device-wide synchronise, i.e. with every gather complete.
-            if gather_out is None:
-                per = K * PackedDetections.WORDS + 1
-                gather_out = dict(stream=torch.cuda.Stream(device=dev), packed=[None, None],
-                                  full=[torch.empty((world * B, per), dtype=torch.int32, device=dev) for _ in range(2)],
-                                  mine=[torch.empty((B, per), dtype=torch.int32, device=dev) for _ in range(2)])
-            slot = i & 1
+    def step(i, marks=None, inputs=None, graph=None):
+        """One step.  N > 1: the decode on the launching stream (from a CUDA graph when given) and the path's one exchange
+        (SURVEY.md 8e), the gather of the fixed-size detections: fused into the select + post kernel (peer-to-peer stores,
+        then a barrier of the ranks on a second stream), or rtm3d_pack_wire + NCCL all-gather on the second stream -- either
+        way behind an event, so that the exchange of batch i overlaps the decode of batch i+1; the timed region ends with a
+        device-wide synchronise, i.e. with every exchange complete."""
+        slot = i & 1
+        p2p = world > 1 and gather_out["mode"] == "p2p"
+        if world > 1 and not capturing and gather_out["gathered"][slot] is not None:
+            torch.cuda.current_stream().wait_event(gather_out["gathered"][slot])    # batch i-2's rows have been exchanged
+        if graph is not None:
+            graph.replay()
+            det = None
+        else:
+            gt = None
+            if p2p and marks is None:
+                gather_out["step_id"] += 1
+                gt = (gather_out["peers"][slot], world, rank, gather_out["step_id"])
+            det = decode(i, decs_dev[i % len(decs_dev)], inputs if inputs is not None else sets[i % nsets], marks, gather=gt)
+            if world > 1 and not p2p:
+                det.to_wire(gather_out["mine"][slot])                                 # one launch of the library (rtm3d_pack_wire)
+        if world > 1 and not capturing:
             ready = torch.cuda.Event()
             ready.record()
             with torch.cuda.stream(gather_out["stream"]):
                 gather_out["stream"].wait_event(ready)
-                wire = det.to_wire(gather_out["mine"][slot])
-                if gather_out["packed"][slot] is None:
-                    gather_out["packed"][slot] = torch.cuda.Event()
-                gather_out["packed"][slot].record()
-                dist.all_gather_into_tensor(gather_out["full"][slot], wire)
+                if p2p:
+                    if marks is None:                                               # every rank's rows of this batch have landed here
+                        _native.check(_native.lib().rtm3d_wait_gather(gather_out["buf"][slot].data_ptr(), B, K, 8, world, gather_out["step_id"],
+                                                                      gather_out["stream"].cuda_stream), "rtm3d_wait_gather")
+                else:
+                    dist.all_gather_into_tensor(gather_out["full"][slot], gather_out["mine"][slot])
+                if gather_out["gathered"][slot] is None:
+                    gather_out["gathered"][slot] = torch.cuda.Event()
+                gather_out["gathered"][slot].record()
         return det
 
     def barrier():
@@ -339,23 +384,34 @@ def run_b200(args, w_job):
         step(i)
     barrier()
 
-    # ---- optional: the step captured in CUDA graphs (one per input set), replayed in the timed region
+    # ---- the kernels of a step replayed from CUDA graphs (one per input set / result slot): N > 1 by default -- the host
+    #      would otherwise need longer to issue a step (kernels, events, pack, all-gather call) than the GPU to run it -- and
+    #      on request at N = 1 (launch-bound small batches).  The collective itself is issued eagerly on the gather stream.
     graphs = None
-    if args.graph:
-        if world > 1:
-            raise SystemExit("bench.py: --graph is a single-GPU option (the gather stream is not captured)")
-        graphs = []
-        for s in range(nsets):
-            gph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gph):
-                step(s)
-            graphs.append(gph)
-        for s in range(nsets):
-            graphs[s].replay()
-        barrier()
+    # (the fused peer-to-peer gather carries a step id per launch: eager steps; its host side is light enough)
+    use_graph = args.graph or (world > 1 and not args.no_graph and gather_out["mode"] == "nccl")
+    if use_graph:
+        try:
+            graphs = []
+            for j in range(2):
+                gph = torch.cuda.CUDAGraph()
+                capturing = True
+                with torch.cuda.graph(gph):
+                    step(j)
+                capturing = False
+                graphs.append(gph)
+            for j in range(2):
+                step(j, graph=graphs[j])
+            barrier()
+        except Exception as e:                       # capture not possible: eager steps
+            capturing = False
+            graphs = None
+            print(f"bench.py: CUDA graph capture failed ({e!r}); eager steps", file=sys.stderr)
+            torch.cuda.synchronize()
 
     # ---- timed region: exactly K steps, CUDA events on the launching stream, per-kernel marks on the same stream
-    marks = [] if graphs is None else None
+    p2p_mode = world > 1 and gather_out["mode"] == "p2p"
+    marks = [] if (graphs is None and not p2p_mode) else None      # (p2p: ONE fused call per step; kernel times from a separate short run)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     e0.record()
@@ -363,7 +419,7 @@ def run_b200(args, w_job):
         if graphs is None:
             step(i, marks)
         else:
-            graphs[i % nsets].replay()
+            step(i, graph=graphs[i & 1])
     e1.record()
     barrier()
     t_wall1 = time.perf_counter()
@@ -383,23 +439,27 @@ def run_b200(args, w_job):
             for j, n in enumerate(names):
                 kernel_ms[n] += marks[s * per + j].elapsed_time(marks[s * per + j + 1])
         kernel_ms = {n: v / args.steps for n, v in kernel_ms.items()}
-    else:                                   # --graph: per-kernel times from a short un-captured run afterwards
+    else:                                   # graph replay: per-kernel times from a short un-captured run afterwards
         m2 = []
         for i in range(8):
             step(i, m2)
-        torch.cuda.synchronize()
+        barrier()
         per = len(names) + 1
         kernel_ms = {n: sum(m2[s * per + j].elapsed_time(m2[s * per + j + 1]) for s in range(8)) / 8 for j, n in enumerate(names)}
 
     # ---- the gather delivers every rank's detections to every rank: check the last two batches on this rank
     verify = None
     if world > 1 and args.verify:
-        torch.cuda.synchronize()
+        barrier()
         ok = True
         for slot in range(2):
-            full, mine = gather_out["full"][slot], gather_out["mine"][slot]
+            # two more (eager) steps: this rank's own wire rows, packed by rtm3d_pack_wire, are the reference for its block
+            det = step(slot)
+            barrier()
+            full = gather_out["full"][slot]
+            mine = det.to_wire()
             ok &= bool(torch.equal(full[rank * B:(rank + 1) * B], mine))                  # my block is my own wire rows
-            sums = full.view(world, -1).to(torch.int64).sum(dim=1)                        # checksum of every rank's block as I received it
+            sums = full.reshape(world, -1).to(torch.int64).sum(dim=1)                      # checksum of every rank's block as I received it
             own = torch.zeros(world, dtype=torch.int64, device=dev)
             own[rank] = mine.to(torch.int64).sum()
             dist.all_reduce(own, op=dist.ReduceOp.SUM)                                     # the checksums the owners computed
@@ -409,8 +469,8 @@ def run_b200(args, w_job):
             ok &= bool(((back.counts >= 0) & (back.counts <= K)).all())
         flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        verify = {"ok": bool(flag.item()), "ranks": world, "rows_per_rank": B,
-                  "what": "all-gathered wire rows == every owner's rows (own block bit-equal, all blocks by checksum), last two batches"}
+        verify = {"ok": bool(flag.item()), "ranks": world, "rows_per_rank": B, "gather": gather_out["mode"],
+                  "what": "gathered wire rows == every owner's rows (own block bit-equal with rtm3d_pack_wire's, all blocks by checksum), both result slots"}
 
     # ---- the kernels keep no state: first launch on a fresh workspace, and batches that alternate between two distributions
     cold_ms = shift_ms = None
@@ -501,7 +561,7 @@ def run_b200(args, w_job):
             "config": config_dict(args.workload, w_job, world, args.scaling, B),
             "inputs": f"{nsets} input sets rotated, {heat_bytes / 1e6:.0f} MB of heat-map per step vs 126 MB L2"
                       + ("" if heat_bytes > 130e6 else " (SMALLER than L2: later steps may hit L2)"),
-            "run": {"cuda_graph": bool(args.graph), "max_ctas": max_ctas},
+            "run": {"cuda_graph": graphs is not None, "max_ctas": max_ctas, "gather": None if world == 1 else gather_out["mode"]},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["gbs"], "peak": peak, "unit": "GB/s",
                          "frac": per_kernel[dom]["frac"], "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
                          "bytes_per_launch": per_kernel[dom]["bytes"],
@@ -513,7 +573,7 @@ def run_b200(args, w_job):
                          "shift_ms_per_step": None if shift_ms is None else round(shift_ms, 5),
                          "state": "none: thresholds come from each strip's own data (no memory across planes or launches)"},
             "e2e": e2e,
-            "gpu_launches": n_launches * args.steps,
+            "gpu_launches": (n_launches + (1 if world > 1 and gather_out["mode"] == "nccl" else 0)) * args.steps,
             "clocks": sampler.summary(t_wall0, t_wall1),
         }
         if cpu_baseline is not None:
@@ -542,8 +602,11 @@ def main():
     ap.add_argument("--dtype", choices=["f32", "bf16"], default="f32", help="element type of the head maps handed to the decode")
     ap.add_argument("--no-e2e", action="store_true", help="device-resident timed loop only (the ncu passes)")
     ap.add_argument("--no-extras", action="store_true", help="skip the cold-launch and distribution-shift measurements")
-    ap.add_argument("--graph", action="store_true", help="replay the step from CUDA graphs (launch-bound small batches)")
+    ap.add_argument("--graph", action="store_true", help="replay the steps from a CUDA graph (default at N > 1; launch-bound small batches at N = 1)")
+    ap.add_argument("--no-graph", action="store_true", help="N > 1: eager steps instead of the graph replay")
     ap.add_argument("--verify", action="store_true", help="N > 1: check the all-gathered detections against every owner's rows")
+    ap.add_argument("--gather", choices=["p2p", "nccl"], default="p2p", help="N > 1: fused peer-to-peer gather (symmetric memory) or pack + NCCL all-gather")
+    ap.add_argument("--nccl-ctas", type=int, default=0, help="N > 1: cap the CTAs of NCCL's kernels (NCCL_MAX_CTAS; 0 = NCCL's choice)")
     ap.add_argument("--max-ctas", type=int, default=-1, help="CTAs of the scan kernel (-1: all SMs at N=1, 144 at N>1)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -198,6 +198,30 @@ int rtm3d_post_fused(const int32_t* flat, const int32_t* counts, const int32_t* 
                      float* kpt_proj, float* kpt_score, int32_t* kpt_j, float* verts_cv, void* stream);
 
 /*
+ * rtm3d_decode_fused + the path's one exchange step (the gather of the fixed-size detections), fused: the
+ * CTAs that compute an image's Tier A rows store its wire rows -- K rows of (cls | score | proj 2 | verts 2V | bbox 4 | flat)
+ * 32-bit words followed by the image's count, the layout of rtm3d_pack_wire -- straight into the gather buffer of EVERY
+ * rank over NVLink.  peer_wire[r] = rank r's gather buffer int32 [n_peers * B, K*(9+2V) + 1] as mapped into THIS process
+ * (peer-to-peer / symmetric memory; peer_wire[rank] is the local buffer); this rank's images land in rows
+ * [rank*B, (rank+1)*B) of each.  No second kernel, no NCCL call on the data path; the caller synchronises the ranks before it
+ * reads a buffer or lets it be overwritten.  Shapes the scan + select kernels do not serve are rejected (RTM3D_ERR_SHAPE).
+ */
+int rtm3d_decode_fused_gather(const void* hm, const void* off, const void* off2, const void* kpt_hm, const void* voff2, int dtype,
+                              int B, int C, int Cv, int H, int W, int n_vert, int K, float thresh, float down,
+                              int64_t* cls, float* score, float* proj, float* verts, float* bbox, int32_t* flat, int32_t* counts,
+                              float* kscore, float* kxy, int32_t* kflat, float* kpt_proj, float* kpt_score, int32_t* kpt_j,
+                              float* verts_cv, void* ws, size_t ws_bytes, unsigned flags,
+                              void* const* peer_wire, int n_peers, int rank, unsigned step_id, void* stream);
+/*
+ * Arrival flags of the fused gather: every gather buffer carries n_peers 32-bit words behind its rows (so a buffer has
+ * n_peers*B*(K*(9+2V)+1) + n_peers words).  With step_id != 0 the last CTA of rtm3d_decode_fused_gather's launch stores
+ * step_id into word [rank] of every peer's flag array once all rows of the batch are visible there.  rtm3d_wait_gather
+ * enqueues a one-thread kernel that returns when all n_peers flags of the LOCAL buffer `wire` have reached step_id
+ * (wrap-safe comparison; bounded wait): behind it the batch of every rank can be read.  Step ids must increase.
+ */
+int rtm3d_wait_gather(const void* wire, int B, int K, int n_vert, int n_peers, unsigned step_id, void* stream);
+
+/*
  * Second half of rtm3d_decode_fused when it was called with RTM3D_FLAG_NO_SELECT (it then stops after the scan kernel, whose
  * per-strip candidate lists stay in the workspace): merges and sorts the lists of every selection problem -- the flat top-K
  * over C*H*W of models/model.py:87-98 and the per-channel top-K of :109-114 -- and runs everything rtm3d_post_fused does, in

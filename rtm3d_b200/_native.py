@@ -40,6 +40,9 @@ SIGNATURES = {
     "rtm3d_decode_keypoints_host": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _u, _vp],
     "rtm3d_decode_fused": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f,
                            _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _u, _vp],
+    "rtm3d_decode_fused_gather": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f,
+                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _u, _vp, _i, _i, _u, _vp],
+    "rtm3d_wait_gather": [_vp, _i, _i, _i, _i, _u, _vp],
     "rtm3d_epilogue_main": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp],
     "rtm3d_epilogue_keypoints": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "rtm3d_decode_fused_host": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _vp,

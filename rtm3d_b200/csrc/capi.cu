@@ -78,8 +78,9 @@ int launch_epilogues(const rtm3d::PlaneParams& q, int dtype, unsigned flags, cud
 // Plane-resident scan kernel + selection: writes score / flat / counts (C > 0) and kscore / kflat (Cv > 0).
 // Returns -1000 when the shape is not eligible for the scan kernel (the caller falls back).
 // post: when given (rtm3d_decode_fused), the selection and everything after it run in ONE kernel behind the scan kernel.
+struct GatherTarget { void* const* peers; int n_peers, rank; uint32_t step_id; size_t flag_offset; };
 int scan_and_select(const rtm3d::PlaneParams& q, const rtm3d::WorkspaceLayout& L, void* ws, int dtype, unsigned flags, cudaStream_t s,
-                    const rtm3d::PostFusedParams* post = nullptr) {
+                    const rtm3d::PostFusedParams* post = nullptr, const GatherTarget* gt = nullptr) {
   unsigned char* base = static_cast<unsigned char*>(ws);
   rtm3d::ScanParams sp{};
   sp.hm_main = q.hm_main; sp.hm_kpt = q.hm_kpt;
@@ -108,7 +109,13 @@ int scan_and_select(const rtm3d::PlaneParams& q, const rtm3d::WorkspaceLayout& L
   if (int e = cuda_fail(rc, "decode (scan kernel) launch")) return e;
   if (flags & RTM3D_FLAG_NO_SELECT) return 0;                       // the caller continues with rtm3d_select_post (bench.py's marks)
   if (post) {
-    rtm3d::SelectPostParams f{sp.cand, sp.cand_count, Sp, cap, q.thresh, q.score, q.flat, q.counts, q.kscore, q.kflat, *post, sp.stats};
+    rtm3d::SelectPostParams f{sp.cand, sp.cand_count, Sp, cap, q.thresh, q.score, q.flat, q.counts, q.kscore, q.kflat, *post, sp.stats, {}, 0, 0, 0u, 0, nullptr};
+    if (gt) {
+      for (int r = 0; r < gt->n_peers; ++r) f.wire_peers[r] = static_cast<int32_t*>(gt->peers[r]);
+      f.n_peers = gt->n_peers; f.wire_rank = gt->rank;
+      f.step_id = gt->step_id; f.flag_offset = gt->flag_offset;
+      f.done_counter = reinterpret_cast<uint32_t*>(base + L.queue_off + 64);
+    }
     return cuda_fail(rtm3d::launch_select_post(f, dtype, s), "decode (select + post kernel) launch");
   }
   rtm3d::SelectParams sel{sp.cand, sp.cand_count, q.B, q.C, q.Cv, q.H, q.W, q.K, Sp, cap, q.thresh, q.score, q.flat, q.counts, q.kscore, q.kflat};
@@ -322,11 +329,14 @@ int rtm3d_decode_keypoints_host(const void* kpt_hm_host, const void* voff2_host,
   return 0;
 }
 
-int rtm3d_decode_fused(const void* hm, const void* off, const void* off2, const void* kpt_hm, const void* voff2, int dtype,
-                       int B, int C, int Cv, int H, int W, int n_vert, int K, float thresh, float down, int64_t* cls,
-                       float* score, float* proj, float* verts, float* bbox, int32_t* flat, int32_t* counts, float* kscore,
-                       float* kxy, int32_t* kflat, float* kpt_proj, float* kpt_score, int32_t* kpt_j, float* verts_cv,
-                       void* ws, size_t ws_bytes, unsigned flags, void* stream) {
+}  // extern "C"
+
+namespace {
+int decode_fused_impl(const void* hm, const void* off, const void* off2, const void* kpt_hm, const void* voff2, int dtype,
+                      int B, int C, int Cv, int H, int W, int n_vert, int K, float thresh, float down, int64_t* cls,
+                      float* score, float* proj, float* verts, float* bbox, int32_t* flat, int32_t* counts, float* kscore,
+                      float* kxy, int32_t* kflat, float* kpt_proj, float* kpt_score, int32_t* kpt_j, float* verts_cv,
+                      void* ws, size_t ws_bytes, unsigned flags, void* stream, const GatherTarget* gt) {
   if (!hm || !off || !off2 || !kpt_hm || !voff2 || !cls || !score || !proj || !verts || !bbox || !flat || !counts || !kscore ||
       !kxy || !kflat || !kpt_proj || !kpt_score || !kpt_j || !ws)
     return fail(RTM3D_ERR_NULL, "NULL pointer argument");
@@ -363,10 +373,12 @@ int rtm3d_decode_fused(const void* hm, const void* off, const void* off2, const 
       const bool one_kernel = !(flags & (RTM3D_FLAG_NO_EPILOGUE | RTM3D_FLAG_NO_GROUP)) && rtm3d::select_post_smem(Cv, K, n_vert) <= 200 * 1024;
       rtm3d::PostFusedParams f{flat, counts, kflat, kscore, off, off2, voff2, B, C, Cv, H, W, n_vert, K, down,
                                cls, proj, verts, bbox, kxy, kpt_proj, kpt_score, kpt_j, verts_cv};
-      rc = scan_and_select(q, L, ws, dtype, flags, s, one_kernel ? &f : nullptr);
+      if (gt && !one_kernel) return fail(RTM3D_ERR_SHAPE, "rtm3d_decode_fused_gather: the stages cannot be separated");
+      rc = scan_and_select(q, L, ws, dtype, flags, s, one_kernel ? &f : nullptr, gt);
       if (rc > 0 || (rc < 0 && rc != -1000)) return rc;
       if (rc == 0 && (one_kernel || (flags & RTM3D_FLAG_NO_SELECT))) return 0;
     }
+    if (gt) return fail(RTM3D_ERR_SHAPE, "rtm3d_decode_fused_gather: the shape is not served by the scan + select kernels");
     if (rc == -1000) {
       if (flags & RTM3D_FLAG_NO_SELECT) return fail(RTM3D_ERR_SHAPE, "RTM3D_FLAG_NO_SELECT: the shape is not served by the scan kernel");
       rc = rtm3d::launch_planes(q, dtype, static_cast<int>((flags >> 8) & 0xFu), (flags & RTM3D_FLAG_NO_SPECULATION) ? 0 : 1,
@@ -403,6 +415,42 @@ int rtm3d_decode_fused(const void* hm, const void* off, const void* off2, const 
   if (flags & RTM3D_FLAG_NO_GROUP) return 0;
   return rtm3d_group_vertices(flat, counts, off, off2, dtype, B, H, W, n_vert, K, kscore, kxy, Cv, down, kpt_proj, kpt_score,
                               kpt_j, verts_cv, stream);
+}
+
+}  // namespace
+
+extern "C" {
+
+int rtm3d_decode_fused(const void* hm, const void* off, const void* off2, const void* kpt_hm, const void* voff2, int dtype,
+                       int B, int C, int Cv, int H, int W, int n_vert, int K, float thresh, float down, int64_t* cls,
+                       float* score, float* proj, float* verts, float* bbox, int32_t* flat, int32_t* counts, float* kscore,
+                       float* kxy, int32_t* kflat, float* kpt_proj, float* kpt_score, int32_t* kpt_j, float* verts_cv,
+                       void* ws, size_t ws_bytes, unsigned flags, void* stream) {
+  return decode_fused_impl(hm, off, off2, kpt_hm, voff2, dtype, B, C, Cv, H, W, n_vert, K, thresh, down, cls, score, proj, verts, bbox, flat,
+                           counts, kscore, kxy, kflat, kpt_proj, kpt_score, kpt_j, verts_cv, ws, ws_bytes, flags, stream, nullptr);
+}
+
+int rtm3d_decode_fused_gather(const void* hm, const void* off, const void* off2, const void* kpt_hm, const void* voff2, int dtype,
+                              int B, int C, int Cv, int H, int W, int n_vert, int K, float thresh, float down, int64_t* cls,
+                              float* score, float* proj, float* verts, float* bbox, int32_t* flat, int32_t* counts, float* kscore,
+                              float* kxy, int32_t* kflat, float* kpt_proj, float* kpt_score, int32_t* kpt_j, float* verts_cv,
+                              void* ws, size_t ws_bytes, unsigned flags, void* const* peer_wire, int n_peers, int rank,
+                              unsigned step_id, void* stream) {
+  if (!peer_wire || n_peers < 1 || n_peers > 8 || rank < 0 || rank >= n_peers) return fail(RTM3D_ERR_SHAPE, "bad gather target (1..8 peers)");
+  for (int r = 0; r < n_peers; ++r)
+    if (!peer_wire[r] || reinterpret_cast<uintptr_t>(peer_wire[r]) % 4) return fail(RTM3D_ERR_NULL, "peer_wire[%d] is NULL or misaligned", r);
+  // the arrival flags live behind the rows: word n_peers*B*(K*(9+2V)+1) of every gather buffer, one word per source rank
+  const GatherTarget gt{peer_wire, n_peers, rank, step_id, static_cast<size_t>(n_peers) * B * (static_cast<size_t>(K) * (9 + 2 * n_vert) + 1)};
+  return decode_fused_impl(hm, off, off2, kpt_hm, voff2, dtype, B, C, Cv, H, W, n_vert, K, thresh, down, cls, score, proj, verts, bbox, flat,
+                           counts, kscore, kxy, kflat, kpt_proj, kpt_score, kpt_j, verts_cv, ws, ws_bytes, flags, stream, &gt);
+}
+
+int rtm3d_wait_gather(const void* wire, int B, int K, int n_vert, int n_peers, unsigned step_id, void* stream) {
+  if (!wire) return fail(RTM3D_ERR_NULL, "NULL pointer argument");
+  if (n_peers < 1 || n_peers > 8 || B < 1 || K < 1) return fail(RTM3D_ERR_SHAPE, "bad gather shape");
+  const size_t flag_offset = static_cast<size_t>(n_peers) * B * (static_cast<size_t>(K) * (9 + 2 * n_vert) + 1);
+  return cuda_fail(rtm3d::launch_wait_flags(static_cast<const uint32_t*>(wire) + flag_offset, n_peers, step_id, static_cast<cudaStream_t>(stream)),
+                   "wait_gather launch");
 }
 
 int rtm3d_epilogue_main(const int32_t* flat, const int32_t* counts, const void* off, const void* off2, int dtype, int B, int C,
@@ -480,7 +528,7 @@ int rtm3d_select_post(const void* off, const void* off2, const void* voff2, int 
 #else
                             nullptr
 #endif
-  };
+                            , {}, 0, 0, 0u, 0, nullptr};
   return cuda_fail(rtm3d::launch_select_post(q, dtype, static_cast<cudaStream_t>(stream)), "select + post kernel launch");
 }
 

@@ -555,6 +555,8 @@ __global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kSpThreads,
   __syncthreads();
   SP_MARK(6);
   // ---- (3) per detection: class, centre, 2D box over the regressed vertices (models/model.py:70-73)
+  const int words = 9 + 2 * V;                                       // wire row: cls | score | proj 2 | verts 2V | bbox 4 | flat
+  int32_t* s_wire = reinterpret_cast<int32_t*>(s_keys);             // [per][words]: the sort area is free by now
   for (int n = n0 + tid; n < n1; n += kSpThreads) {
     const size_t row = static_cast<size_t>(b) * K + n;
     const int nl = n - n0;
@@ -570,10 +572,62 @@ __global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kSpThreads,
         lo_y = fminf(lo_y, vy); hi_y = fmaxf(hi_y, vy);
       }
     }
+    const float px = valid ? __fmul_rn(p.down, s_det[n].mx) : 0.f, py = valid ? __fmul_rn(p.down, s_det[n].my) : 0.f;
     p.cls[row] = c;
-    p.proj[row * 2] = valid ? __fmul_rn(p.down, s_det[n].mx) : 0.f;
-    p.proj[row * 2 + 1] = valid ? __fmul_rn(p.down, s_det[n].my) : 0.f;
+    p.proj[row * 2] = px;
+    p.proj[row * 2 + 1] = py;
     p.bbox[row * 4 + 0] = lo_x; p.bbox[row * 4 + 1] = lo_y; p.bbox[row * 4 + 2] = hi_x; p.bbox[row * 4 + 3] = hi_y;
+    if (sp.n_peers > 0) {
+      int32_t* wr = s_wire + nl * words;
+      wr[0] = c;
+      wr[1] = __float_as_int(valid ? sp.score[row] : 0.f);
+      wr[2] = __float_as_int(px); wr[3] = __float_as_int(py);
+      for (int v = 0; v < 2 * V; ++v) wr[4 + v] = __float_as_int(s_v[nl * V * 2 + v]);
+      wr[4 + 2 * V] = __float_as_int(lo_x); wr[5 + 2 * V] = __float_as_int(lo_y);
+      wr[6 + 2 * V] = __float_as_int(hi_x); wr[7 + 2 * V] = __float_as_int(hi_y);
+      wr[8 + 2 * V] = valid ? s_det[n].flat : -1;
+    }
+  }
+  if (sp.n_peers > 0) {
+    // ---- (4) the path's one exchange, fused: this CTA's wire rows go straight into every peer's gather
+    //      buffer (posted stores over NVLink; the rows of image b of rank r start at word ((r*B + b) * (K*words + 1))
+    __syncthreads();
+    const size_t per_img = static_cast<size_t>(K) * words + 1;
+    const size_t img0 = (static_cast<size_t>(sp.wire_rank) * p.B + b) * per_img;
+    const int n_words = (n1 - n0) * words;
+    // (16-byte stores for the aligned body of the CTA's block of rows, scalar head and tail: remote stores are packets)
+    const size_t s0 = img0 + static_cast<size_t>(n0) * words;
+    for (int r = 0; r < sp.n_peers; ++r) {
+      int32_t* dst = sp.wire_peers[r] + s0;
+      const int to16 = static_cast<int>(((16u - (reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u) >> 2);   // words up to the next 16-byte boundary
+      const int head = to16 < n_words ? to16 : n_words;
+      const int body4 = (n_words - head) >> 2;
+      const int tail0 = head + body4 * 4;
+      if (tid < head) dst[tid] = s_wire[tid];
+      for (int q4 = tid; q4 < body4; q4 += kSpThreads) {
+        const int i = head + q4 * 4;
+        *reinterpret_cast<int4*>(dst + i) = make_int4(s_wire[i], s_wire[i + 1], s_wire[i + 2], s_wire[i + 3]);
+      }
+      if (tid < n_words - tail0) dst[tail0 + tid] = s_wire[tail0 + tid];
+      if (rank == 0 && tid == 0) sp.wire_peers[r][img0 + static_cast<size_t>(K) * words] = n_det;
+    }
+    if (sp.step_id != 0u) {
+      // arrival flag: every CTA makes its remote stores visible system-wide and counts itself; the last one of the launch
+      // then tells every peer that ALL rows of this rank's batch have landed (release pattern: rows, fence, flag)
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence_system();
+        const uint32_t prev = atomicAdd(sp.done_counter, 1u);
+        if (prev == gridDim.x - 1u) {
+          *sp.done_counter = 0u;                                     // clean for the next launch
+          __threadfence_system();
+          for (int r = 0; r < sp.n_peers; ++r) {
+            volatile uint32_t* fl = reinterpret_cast<volatile uint32_t*>(sp.wire_peers[r] + sp.flag_offset);
+            fl[sp.wire_rank] = sp.step_id;
+          }
+        }
+      }
+    }
   }
   SP_MARK(7);
 }
@@ -848,6 +902,23 @@ int launch_box3d(const Box3dParams& p, int dtype, cudaStream_t s) {
   dim3 grid((p.K + 127) / 128, p.B);
   if (dtype == 0) box3d_kernel<float><<<grid, 128, 0, s>>>(p);
   else box3d_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// One thread waits until every rank's arrival flag has reached `value` (the rows of that batch have landed in this rank's
+// gather buffer).  Bounded: a lost peer surfaces as a launch failure, not as a hung GPU.
+__global__ void wait_flags_kernel(const uint32_t* flags, int n, uint32_t value) {
+  const long long t0 = clock64();
+  for (int r = 0; r < n; ++r) {
+    while (static_cast<int32_t>(*reinterpret_cast<const volatile uint32_t*>(flags + r) - value) < 0) {
+      __nanosleep(200);
+      if (clock64() - t0 > 20000000000LL) __trap();
+    }
+  }
+  __threadfence_system();
+}
+int launch_wait_flags(const uint32_t* flags, int n, uint32_t value, cudaStream_t s) {
+  wait_flags_kernel<<<1, 1, 0, s>>>(flags, n, value);
   return static_cast<int>(cudaGetLastError());
 }
 

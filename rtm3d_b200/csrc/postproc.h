@@ -56,7 +56,17 @@ struct SelectPostParams {
   float* score; int32_t* flat; int32_t* counts; float* kscore; int32_t* kflat;     // the selection (written here)
   PostFusedParams post;                                                             // maps, shapes, outputs of the epilogues
   unsigned long long* stats;                                                        // developer timestamps (nullable)
+  // fused gather (rtm3d_decode_fused_gather): the wire rows of this rank's detections are stored straight into every
+  // peer's gather buffer (peer-mapped pointers over NVLink) by the CTAs that compute them; n_peers = 0: no gather
+  int32_t* wire_peers[8];
+  int n_peers, wire_rank;
+  // ... and, when step_id != 0, the arrival flag: the last CTA of the launch stores step_id into word [wire_rank] of every
+  // peer's flag array behind the rows (the flag array starts at word flag_offset of each gather buffer)
+  uint32_t step_id;
+  size_t flag_offset;
+  uint32_t* done_counter;      // workspace word, 0 between launches
 };
+int launch_wait_flags(const uint32_t* flags, int n, uint32_t value, cudaStream_t s);
 size_t select_post_smem(int Cv, int K, int n_vert);
 int launch_select_post(const SelectPostParams& p, int dtype, cudaStream_t s);
 size_t post_fused_smem(int Cv, int K, int n_vert);

@@ -273,14 +273,16 @@ class HeatmapDecoder:
         _native.check(rc, "rtm3d_group_vertices")
         return out
 
-    def decode_with_keypoints(self, pred_logits, kpt_logits, marks=None, fused=True):
+    def decode_with_keypoints(self, pred_logits, kpt_logits, marks=None, fused=True, gather=None):
         """Tier A + Tier B as the commented wiring of models/model.py:45-62,68-69 describes.  Returns
         (PackedDetections, KeypointCandidates, GroupedKeypoints), all asynchronous.  ``fused`` (default): one call of
         ``rtm3d_decode_fused`` -- both heat-maps streamed by a single kernel launch, then the grouping kernel; otherwise
         the three separate entry points.  ``marks``: optional list that receives a recorded ``torch.cuda.Event`` before
         the plane-streaming kernel and after the epilogue and grouping kernels (bench.py times the kernels with it; the
         fused call is then issued as selection-only ``rtm3d_decode_fused`` + ``rtm3d_post_fused``: the same two launches
-        with an event in between)."""
+        with an event in between).  ``gather`` = (ctypes array of peer-mapped gather buffers, n_peers, rank, step id of the arrival flag or 0): the wire rows
+        of the detections are stored straight into every rank's gather buffer by the select + post kernel
+        (``rtm3d_decode_fused_gather``: the path's one exchange, fused; no pack kernel, no collective call)."""
         def mark():
             if marks is not None:
                 e = torch.cuda.Event(enable_timing=True)
@@ -327,6 +329,19 @@ class HeatmapDecoder:
                     self._out[okey] = (det, cand, grp)
             else:
                 det, cand, grp = cached
+            if gather is not None:
+                if marks is not None:
+                    raise ValueError("gather and marks cannot be combined (the fused gather is one call)")
+                peers, n_peers, rank, step_id = gather
+                rc = self._lib.rtm3d_decode_fused_gather(
+                    main.data_ptr(), off.data_ptr(), off2.data_ptr(), kpt_logits.data_ptr(), voff2.data_ptr(), dt,
+                    B, C, Cv, H, W, V, K, self.score_thresh, self.down_sample,
+                    det.cls.data_ptr(), det.score.data_ptr(), det.proj.data_ptr(), det.verts.data_ptr(), det.bbox.data_ptr(),
+                    det.flat.data_ptr(), det.counts.data_ptr(), cand.score.data_ptr(), cand.xy.data_ptr(), cand.flat.data_ptr(),
+                    grp.kpt_proj.data_ptr(), grp.kpt_score.data_ptr(), grp.kpt_j.data_ptr(), grp.verts.data_ptr(),
+                    ws.data_ptr(), ws.numel(), self.flags, peers, n_peers, rank, step_id, stream)
+                _native.check(rc, "rtm3d_decode_fused_gather")
+                return det, cand, grp
             mark()
             legacy = bool(self.flags & (_native.FLAG_LEGACY_PLANES | _native.FLAG_FORCE_GENERIC))
             # marks: the same two launches as the unmarked call, issued separately with an event in between -- scan kernel, then
