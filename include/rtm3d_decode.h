@@ -265,6 +265,25 @@ int rtm3d_decode_box3d(const int32_t* flat, const int32_t* counts, const void* r
                        float* loc, float* dim, float* alpha, float* rot_y, float* corners2d, void* stream);
 
 /*
+ * Batched 3D-box fit: the step right behind the decoder in detect.py (:71-74), replacing optim_decode_bbox3d
+ * (utils/model_utils.py:264-312: one scipy L-BFGS-B run per object).  Per detection the reference's reprojection objective
+ * (aimFun :155-177) is minimised from the reference's start point [0, 1, l_ref, h_ref, w_ref] + ref_loc (:290) by
+ * Levenberg-Marquardt in double precision (analytic Jacobian, the derivatives of :206-234) and accepted when f < 0.1 (:298).
+ *   verts  f32 [B,K,8,2]  v_projs_regress (input pixels)      cls int64 [B,K]      counts int32 [B] (NULL: all K rows)
+ *   cam    f32 [B,9] (cam_per_image != 0) or [9]: row-major camera matrix      dim_ref f32 [n_classes,3] (h,w,l)
+ *   ref_loc: 3 floats in HOST memory (detect.py:74 passes 0, -0.5, 20)
+ * Outputs (rows >= counts[b]: zeros, accept 0):
+ *   loc f32 [B,K,3]   dim f32 [B,K,3] = (h,w,l) (:301)   ry f32 [B,K] = atan2(sin, cos) (:299)   fun f32 [B,K]
+ *   accept int32 [B,K] = (fun < 0.1)   x8 f64 [B,K,8] raw solution [sin,cos,l,h,w,X,Y,Z] (may be NULL)   iters int32 [B,K] (may be NULL)
+ * The objective leaves a two-parameter family of minimisers (rotation-vector length; common scale of dimensions and
+ * location): dim / loc are reported for the member with sin^2+cos^2 = 1 whose dimensions are closest to the class prior;
+ * fun, accept, ry, the reprojected corners and all ratios of (l,h,w,X,Y,Z) are independent of that choice.
+ */
+int rtm3d_fit_box3d(const float* verts, const int64_t* cls, const int32_t* counts, const float* cam, int cam_per_image,
+                    const float* dim_ref, int n_classes, const float* ref_loc, int B, int K, int max_iter,
+                    float* loc, float* dim, float* ry, float* fun, int32_t* accept, double* x8, int32_t* iters, void* stream);
+
+/*
  * Packs the Tier A result of a batch into the wire rows of the multi-GPU gather (the path's one collective):
  * wire int32 [B][K*(9+2*n_vert) + 1] = per image K rows of (cls | score | proj 2 | verts 2*n_vert | bbox 4 | flat) as
  * 32-bit patterns, then counts[b].  One launch instead of a chain of torch cat / cast kernels.

@@ -576,6 +576,17 @@ int rtm3d_decode_box3d(const int32_t* flat, const int32_t* counts, const void* r
   return cuda_fail(rtm3d::launch_box3d(q, dtype, static_cast<cudaStream_t>(stream)), "box3d launch");
 }
 
+int rtm3d_fit_box3d(const float* verts, const int64_t* cls, const int32_t* counts, const float* cam, int cam_per_image,
+                    const float* dim_ref, int n_classes, const float* ref_loc, int B, int K, int max_iter, float* loc, float* dim,
+                    float* ry, float* fun, int32_t* accept, double* x8, int32_t* iters, void* stream) {
+  if (!verts || !cls || !cam || !dim_ref || !ref_loc || !loc || !dim || !ry || !fun || !accept) return fail(RTM3D_ERR_NULL, "NULL pointer argument");
+  if (B < 1 || K < 1 || n_classes < 1 || static_cast<long long>(B) * K > (1LL << 30)) return fail(RTM3D_ERR_SHAPE, "bad shape B=%d K=%d", B, K);
+  if (max_iter < 1) max_iter = 100;
+  rtm3d::BoxFitParams q{verts, cls, counts, cam, cam_per_image ? 1 : 0, dim_ref, {ref_loc[0], ref_loc[1], ref_loc[2]}, B, K, max_iter,
+                        loc, dim, ry, fun, accept, x8, iters};
+  return cuda_fail(rtm3d::launch_fit_box3d(q, static_cast<cudaStream_t>(stream)), "fit_box3d launch");
+}
+
 int rtm3d_pack_wire(const int64_t* cls, const float* score, const float* proj, const float* verts, const float* bbox,
                     const int32_t* flat, const int32_t* counts, int B, int K, int n_vert, int32_t* wire, void* stream) {
   if (!cls || !score || !proj || !verts || !bbox || !flat || !counts || !wire) return fail(RTM3D_ERR_NULL, "NULL pointer argument");

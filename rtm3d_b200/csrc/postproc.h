@@ -66,6 +66,21 @@ struct SelectPostParams {
   size_t flag_offset;
   uint32_t* done_counter;      // workspace word, 0 between launches
 };
+// Batched 3D-box fit behind the decoder (boxfit.cu; utils/model_utils.py:264-312).
+struct BoxFitParams {
+  const float* verts;      // [B,K,8,2] regressed vertices, input pixels (v_projs_regress)
+  const int64_t* cls;      // [B,K]
+  const int32_t* counts;   // [B] valid detections per image (nullptr: all K)
+  const float* cam;        // [B,9] or [1,9] row-major camera matrix
+  int cam_per_image;
+  const float* dim_ref;    // [C,3] class priors (h, w, l)
+  float ref_loc[3];        // start location (detect.py:74: 0, -0.5, 20)
+  int B, K, max_iter;
+  float* loc; float* dim; float* ry; float* fun; int32_t* accept;   // [B,K,3] [B,K,3] (h,w,l) [B,K] [B,K] [B,K]
+  double* x8;              // [B,K,8] raw solution vector (nullable)
+  int32_t* iters;          // [B,K] iterations used (nullable)
+};
+int launch_fit_box3d(const BoxFitParams& p, cudaStream_t s);
 int launch_wait_flags(const uint32_t* flags, int n, uint32_t value, cudaStream_t s);
 size_t select_post_smem(int Cv, int K, int n_vert);
 int launch_select_post(const SelectPostParams& p, int dtype, cudaStream_t s);

@@ -47,6 +47,23 @@ def install(model_cls) -> None:
     model_cls.forward = _forward
 
 
+def install_boxfit(model_utils_module, device="cuda:0") -> None:
+    """Rebind ``utils.model_utils.optim_decode_bbox3d`` (utils/model_utils.py:264-312, called at detect.py:71-74) to the batched
+    GPU fit: same arguments, and a result whose ``get_field`` serves 'class', 'Ry', 'dimension', 'location', 'K' like the
+    reference's ParamList."""
+    from .boxfit import optim_decode_bbox3d
+    if model_utils_module in _ORIG:
+        return
+    _ORIG[model_utils_module] = (model_utils_module.optim_decode_bbox3d,)
+    model_utils_module.optim_decode_bbox3d = lambda clses, projs, K, ref_dim, ref_loc: optim_decode_bbox3d(clses, projs, K, ref_dim, ref_loc, device=device)
+
+
+def uninstall_boxfit(model_utils_module) -> None:
+    orig = _ORIG.pop(model_utils_module, None)
+    if orig:
+        model_utils_module.optim_decode_bbox3d = orig[0]
+
+
 def uninstall(model_cls) -> None:
     orig = _ORIG.pop(model_cls, None)
     if orig:
