@@ -284,6 +284,27 @@ int rtm3d_fit_box3d(const float* verts, const int64_t* cls, const int32_t* count
                     float* loc, float* dim, float* ry, float* fun, int32_t* accept, double* x8, int32_t* iters, void* stream);
 
 /*
+ * Training-side mirror of the decoder.
+ * rtm3d_encode_main_targets: the m_hm part of DatasetReader._build_targets (datasets/dataset_reader.py:215-291) with
+ *   data_utils.dynamic_radius / gaussian2D (utils/data_utils.py:97-141): per labelled object (mask != 0) the centre of its 2D box
+ *   (heat-map units), a Gaussian of the box's radius splatted with max into plane (img_id, cls); the centre of a noise object
+ *   is 0.9999 (:262-263).  m_hm f32 [B,C,H,W] is zeroed and filled here; m_proj int32 [N,2], m_off f32 [N,2] (:225-228),
+ *   sigma f32 [N], radius int32 [N] are the per-object by-products the reader keeps.
+ * rtm3d_focal_loss: FocalLoss.forward (models/nets/module.py:41-68) on sigmoid_hm(logits) (utils/model_utils.py:10-14), the
+ *   main heat-map loss of models/rtm3d_loss.py:283: loss f32 [1]; acc = 3 doubles of device scratch (positive sum, negative
+ *   sum, number of positives) that rtm3d_focal_loss_grad reads.
+ * rtm3d_focal_loss_grad: grad[i] = upstream * d loss / d logits[i] (what autograd yields for the reference); upstream = device
+ *   pointer to the incoming gradient of the loss (NULL: 1).
+ */
+int rtm3d_encode_main_targets(const float* bbox, const int64_t* cls, const int64_t* img_id, const uint8_t* mask,
+                              const uint8_t* noise_mask, int N, int B, int C, int H, int W, float* m_hm, int32_t* m_proj,
+                              float* m_off, float* sigma, int32_t* radius, void* stream);
+int rtm3d_focal_loss(const float* logits, const float* target, size_t n, float alpha, float beta, double* acc, float* loss,
+                     void* stream);
+int rtm3d_focal_loss_grad(const float* logits, const float* target, size_t n, float alpha, float beta, const double* acc,
+                          const float* upstream, float* grad, void* stream);
+
+/*
  * Packs the Tier A result of a batch into the wire rows of the multi-GPU gather (the path's one collective):
  * wire int32 [B][K*(9+2*n_vert) + 1] = per image K rows of (cls | score | proj 2 | verts 2*n_vert | bbox 4 | flat) as
  * 32-bit patterns, then counts[b].  One launch instead of a chain of torch cat / cast kernels.

@@ -587,6 +587,28 @@ int rtm3d_fit_box3d(const float* verts, const int64_t* cls, const int32_t* count
   return cuda_fail(rtm3d::launch_fit_box3d(q, static_cast<cudaStream_t>(stream)), "fit_box3d launch");
 }
 
+int rtm3d_encode_main_targets(const float* bbox, const int64_t* cls, const int64_t* img_id, const uint8_t* mask, const uint8_t* noise_mask,
+                              int N, int B, int C, int H, int W, float* m_hm, int32_t* m_proj, float* m_off, float* sigma, int32_t* radius,
+                              void* stream) {
+  if (!m_hm || (N > 0 && (!bbox || !cls || !img_id || !mask || !noise_mask || !m_proj || !m_off || !sigma || !radius)))
+    return fail(RTM3D_ERR_NULL, "NULL pointer argument");
+  if (N < 0 || B < 1 || C < 1 || H < 1 || W < 1) return fail(RTM3D_ERR_SHAPE, "bad shape N=%d B=%d C=%d H=%d W=%d", N, B, C, H, W);
+  rtm3d::TargetParams q{bbox, cls, img_id, mask, noise_mask, N, B, C, H, W, m_hm, m_proj, m_off, sigma, radius};
+  return cuda_fail(rtm3d::launch_encode_targets(q, static_cast<cudaStream_t>(stream)), "encode_targets launch");
+}
+
+int rtm3d_focal_loss(const float* logits, const float* target, size_t n, float alpha, float beta, double* acc, float* loss, void* stream) {
+  if (!logits || !target || !acc || !loss) return fail(RTM3D_ERR_NULL, "NULL pointer argument");
+  if (reinterpret_cast<uintptr_t>(acc) % 8) return fail(RTM3D_ERR_ALIGN, "acc must be 8-byte aligned");
+  return cuda_fail(rtm3d::launch_focal_loss(logits, target, n, alpha, beta, acc, loss, static_cast<cudaStream_t>(stream)), "focal_loss launch");
+}
+
+int rtm3d_focal_loss_grad(const float* logits, const float* target, size_t n, float alpha, float beta, const double* acc,
+                          const float* upstream, float* grad, void* stream) {
+  if (!logits || !target || !acc || !grad) return fail(RTM3D_ERR_NULL, "NULL pointer argument");
+  return cuda_fail(rtm3d::launch_focal_grad(logits, target, n, alpha, beta, acc, upstream, grad, static_cast<cudaStream_t>(stream)), "focal_loss_grad launch");
+}
+
 int rtm3d_pack_wire(const int64_t* cls, const float* score, const float* proj, const float* verts, const float* bbox,
                     const int32_t* flat, const int32_t* counts, int B, int K, int n_vert, int32_t* wire, void* stream) {
   if (!cls || !score || !proj || !verts || !bbox || !flat || !counts || !wire) return fail(RTM3D_ERR_NULL, "NULL pointer argument");

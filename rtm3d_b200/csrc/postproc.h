@@ -81,6 +81,24 @@ struct BoxFitParams {
   int32_t* iters;          // [B,K] iterations used (nullable)
 };
 int launch_fit_box3d(const BoxFitParams& p, cudaStream_t s);
+// Training-side mirror (train_side.cu): main heat-map target encoder and focal loss.
+struct TargetParams {
+  const float* bbox;       // [N,4] 2D boxes x1,y1,x2,y2 in HEAT-MAP units (targets' bbox / DOWN_SAMPLE)
+  const int64_t* cls;      // [N]
+  const int64_t* img_id;   // [N] image of the batch
+  const uint8_t* mask;     // [N] labelled main point
+  const uint8_t* noise_mask;   // [N]
+  int N, B, C, H, W;
+  float* m_hm;             // [B,C,H,W] out (zeroed here)
+  int32_t* m_proj;         // [N,2] integer centre (x,y)
+  float* m_off;            // [N,2] sub-pixel offset of the centre
+  float* sigma;            // [N]
+  int32_t* radius;         // [N]
+};
+int launch_encode_targets(const TargetParams& p, cudaStream_t s);
+int launch_focal_loss(const float* logits, const float* target, size_t n, float alpha, float beta, double* acc, float* loss, cudaStream_t s);
+int launch_focal_grad(const float* logits, const float* target, size_t n, float alpha, float beta, const double* acc, const float* upstream,
+                      float* grad, cudaStream_t s);
 int launch_wait_flags(const uint32_t* flags, int n, uint32_t value, cudaStream_t s);
 size_t select_post_smem(int Cv, int K, int n_vert);
 int launch_select_post(const SelectPostParams& p, int dtype, cudaStream_t s);
