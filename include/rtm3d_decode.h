@@ -187,7 +187,7 @@ int rtm3d_epilogue_keypoints(const int32_t* kflat, const void* voff2, int dtype,
                              float* kxy, void* stream);
 
 /*
- * Everything that follows the selection of rtm3d_decode_fused in ONE kernel (one CTA per image): rtm3d_epilogue_keypoints,
+ * Everything that follows the selection of rtm3d_decode_fused in ONE kernel (a cluster of CTAs per image): rtm3d_epilogue_keypoints,
  * rtm3d_epilogue_main and rtm3d_group_vertices with bit-identical results.  rtm3d_decode_fused enqueues it itself unless
  * RTM3D_FLAG_NO_EPILOGUE / RTM3D_FLAG_NO_GROUP ask for the stages separately.
  */

@@ -14,6 +14,21 @@
 
 namespace rtm3d {
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) costs a driver call: made once per (kernel, device), and again only when
+// a launch asks for more than the kernel was granted before.
+template <auto Kern>
+inline cudaError_t ensure_dynamic_smem(size_t bytes) {
+  static int granted[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool tracked = dev >= 0 && dev < 64;
+  if (tracked && granted[dev] >= static_cast<int>(bytes)) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  if (e == cudaSuccess && tracked) granted[dev] = static_cast<int>(bytes);
+  return e;
+}
+
+
 constexpr int kMaxTopK = 1024;
 constexpr int kMaxVerts = 16;
 

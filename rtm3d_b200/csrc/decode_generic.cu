@@ -182,7 +182,7 @@ WorkspaceLayout workspace_layout(int B, int C, int H, int W, int K) {
 template <typename T, int MODE>
 static int launch_generic_t(const DecodeParams& p, size_t smem, cudaStream_t s) {
   auto kern = decode_generic_kernel<T, MODE>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  cudaError_t e = ensure_dynamic_smem<decode_generic_kernel<T, MODE>>(smem);
   if (e != cudaSuccess) return static_cast<int>(e);
   dim3 grid(p.nstrips * p.C, p.B);
   kern<<<grid, kGenericThreads, smem, s>>>(p);

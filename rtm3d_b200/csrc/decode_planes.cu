@@ -1189,6 +1189,7 @@ static bool make_plane_geom(const PlaneParams& p, int dtype, int split_override,
   if ((p.hm_main && reinterpret_cast<uintptr_t>(p.hm_main) % 16 != 0) || (p.hm_kpt && reinterpret_cast<uintptr_t>(p.hm_kpt) % 16 != 0)) return false;
   const int row_bytes = p.W * es;
   if (row_bytes > 8192) return false;
+  if (row_bytes < 32) return false;                        // a one-group row: ceil(2^32 / gpr) does not fit the 32-bit magic (generic kernels)
   const int g_sm_count = plane_sm_count();
   if (g_sm_count <= 0) return false;
   const long long planes = static_cast<long long>(p.B) * ((p.C > 0 ? 1 : 0) + p.Cv);   // items per strip index (the C main planes are one item)
@@ -1271,7 +1272,7 @@ bool planes_eligible(const PlaneParams& p, int dtype) {
 template <typename T, bool STATS, bool DBG, bool SPLIT>
 static int launch_planes_t(const PlaneParams& p, const PlaneGeom& g, cudaStream_t s) {
   auto kern = decode_planes_kernel<T, STATS, DBG, SPLIT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.smem));
+  cudaError_t e = ensure_dynamic_smem<decode_planes_kernel<T, STATS, DBG, SPLIT>>(g.smem);
   if (e != cudaSuccess) return static_cast<int>(e);
   const int g_sm_count = plane_sm_count();
   int grid = g.n_items < g_sm_count ? g.n_items : g_sm_count;

@@ -684,11 +684,11 @@ int launch_post_fused(const PostFusedParams& p, int dtype, cudaStream_t s) {
   const unsigned grid = static_cast<unsigned>(p.B) * kPostSplit;
   cudaError_t e;
   if (dtype == 0) {
-    e = cudaFuncSetAttribute(post_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    e = ensure_dynamic_smem<post_fused_kernel<float>>(smem);
     if (e != cudaSuccess) return static_cast<int>(e);
     post_fused_kernel<float><<<grid, kPostThreads, smem, s>>>(p);
   } else {
-    e = cudaFuncSetAttribute(post_fused_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    e = ensure_dynamic_smem<post_fused_kernel<__nv_bfloat16>>(smem);
     if (e != cudaSuccess) return static_cast<int>(e);
     post_fused_kernel<__nv_bfloat16><<<grid, kPostThreads, smem, s>>>(p);
   }
@@ -757,11 +757,11 @@ int launch_group(const GroupParams& p, int dtype, cudaStream_t s) {
   const size_t smem = static_cast<size_t>(p.Cv) * p.K * 2 * sizeof(float);
   cudaError_t e;
   if (dtype == 0) {
-    e = cudaFuncSetAttribute(group_vertices_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    e = ensure_dynamic_smem<group_vertices_kernel<float>>(smem);
     if (e != cudaSuccess) return static_cast<int>(e);
     group_vertices_kernel<float><<<p.B, 256, smem, s>>>(p);
   } else {
-    e = cudaFuncSetAttribute(group_vertices_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    e = ensure_dynamic_smem<group_vertices_kernel<__nv_bfloat16>>(smem);
     if (e != cudaSuccess) return static_cast<int>(e);
     group_vertices_kernel<__nv_bfloat16><<<p.B, 256, smem, s>>>(p);
   }

@@ -36,7 +36,7 @@ struct EpiKptParams {
 };
 int launch_epilogue_main(const EpiMainParams& p, int dtype, cudaStream_t s);
 int launch_epilogue_kpt(const EpiKptParams& p, int dtype, cudaStream_t s);
-// Everything after the selection of a fused decode in ONE kernel (one CTA per image): Tier B epilogue, Tier A epilogue
+// Everything after the selection of a fused decode in ONE kernel (a cluster of CTAs per image): Tier B epilogue, Tier A epilogue
 // and the keypoint grouping.
 struct PostFusedParams {
   const int32_t* flat; const int32_t* counts; const int32_t* kflat; const float* kscore;

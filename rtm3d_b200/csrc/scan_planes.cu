@@ -718,6 +718,7 @@ bool make_scan_geom(int B, int C, int Cv, int H, int W, int K, int dtype, int st
   g.row_bytes = W * es;
   g.gpr = g.row_bytes / 16;
   if (g.gpr > kChunkGroups) return false;                  // one row must fit a chunk
+  if (g.gpr < 2) return false;                             // a one-group row: ceil(2^32 / gpr) does not fit the 32-bit magic (generic kernels)
   g.slot_rows = kChunkGroups / g.gpr;
   if (g.slot_rows > H) g.slot_rows = H;
   g.slot_bytes = g.slot_rows * g.row_bytes;
