@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
   if (fast) {
     // one warp per list (register sort), then the rank-merge of the problem's lists
     for (int t = warp; t < n_lists; t += kSelThreads / 32) {
-      const int cnt = warp_sort_list(p.cand, p.cand_count, p.list_cap, first + t, lim, keys + t * kFastPad, lane);
+      const int cnt = warp_sort_list(p.cand, p.cand_count, p.list_cap, first + t, lim, p.K, keys + t * kFastPad, lane);
       if (lane == 0) s_cnt[t] = cnt;
     }
     __syncthreads();

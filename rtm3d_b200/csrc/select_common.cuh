@@ -141,47 +141,85 @@ __device__ __forceinline__ int count_greater_u64(const uint64_t* r, int len, uin
   return lo;
 }
 
-// One warp: the kFastPad best (score, index) keys of candidate list `strip`, sorted, into dst[0..kFastPad) (zeros behind the
-// valid ones); returns min(valid, kFastPad).  (logit, index) keys become (score, index) keys here -- the sigmoid of
-// models/model.py:85,107 for the listed pixels -- and pixels at or below the score floor `lim` drop out.  The first round
-// takes 256 keys; a longer list goes on in rounds of 128 new keys merged with the 128 best so far.
+// One warp: the best (score, index) keys of candidate list `strip`, sorted, into dst[0..kFastPad) (zeros behind the valid
+// ones); returns the number of valid keys stored (<= kFastPad).  Only the list's K best matter to the caller (K <= kFastPad):
+// dst[0..min(K, valid)) are exactly the list's best, what follows is sorted and smaller but need not be the next best.
+// (logit, index) keys become (score, index) keys here -- the sigmoid of models/model.py:85,107 for the listed pixels -- and
+// pixels at or below the score floor `lim` drop out.  The first 256 keys go through the register sort; a longer list goes on
+// in rounds of 128 new keys, of which only those above the K-th best so far are inserted (one shuffle + four
+// compare-selects per lane and insertion: a list of 300 keys inserts ~17, a second full sort would cost as much as the first).
 __device__ __forceinline__ int warp_sort_list(const unsigned long long* cand, const uint32_t* cand_count, int list_cap, int strip, float lim,
-                                              uint64_t* dst, int lane) {
+                                              int K, uint64_t* dst, int lane) {
   const uint32_t raw = cand_count[strip];
   const int cnt = static_cast<int>(raw & ~kCandScoreKeys);
   const bool score_keys = (raw & kCandScoreKeys) != 0u;
   const unsigned long long* src = cand + static_cast<size_t>(strip) * list_cap;
-  int valid = 0;
-  for (int base = 0; base == 0 || base < cnt; base += (base == 0 ? kFastKeys : kFastPad)) {
+  auto load_key = [&](int i) -> unsigned long long {
+    unsigned long long key = 0ull;
+    if (i < cnt) {
+      key = src[i];
+      if (!score_keys) {
+        const float sc = sigmoid_ref(f32_unord(static_cast<uint32_t>(key >> 32)));
+        key = sc > lim ? make_key(sc, key_flat(key)) : 0ull;
+      }
+    }
+    return key;
+  };
+  int stored;
+  {
     unsigned long long x[8];
+    int valid = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      unsigned long long key = 0ull;
-      if (base != 0 && k < 4) {
-        key = dst[k * 32 + lane];                                // the best so far (any order)
-      } else {
-        const int i = base + (base == 0 ? k : k - 4) * 32 + lane;
-        if (i < cnt) {
-          key = src[i];
-          if (!score_keys) {
-            const float sc = sigmoid_ref(f32_unord(static_cast<uint32_t>(key >> 32)));
-            key = sc > lim ? make_key(sc, key_flat(key)) : 0ull;
-          }
-        }
-        valid += key != 0ull ? 1 : 0;
-      }
-      x[k] = key;
+      x[k] = load_key(k * 32 + lane);
+      valid += x[k] != 0ull ? 1 : 0;
     }
     warp_sort256_desc(x, lane);
-    __syncwarp();
     if (lane < kFastPad / 8) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) dst[lane * 8 + k] = x[k];
     }
     __syncwarp();
+    stored = min(__reduce_add_sync(0xffffffffu, valid), kFastPad);
   }
-  valid = __reduce_add_sync(0xffffffffu, valid);
-  return min(valid, kFastPad);
+  if (cnt > kFastKeys) {
+    // r[i] = dst[4 * lane + i]: the sorted list, four consecutive keys per lane
+    unsigned long long r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = dst[4 * lane + i];
+    for (int base = kFastKeys; base < cnt; base += kFastPad) {
+      const unsigned long long pivot = stored >= K ? dst[K - 1] : 0ull;      // (dst is current: written back after every round)
+      unsigned long long x[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) x[k] = load_key(base + k * 32 + lane);
+      int inserted = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        unsigned mask = __ballot_sync(0xffffffffu, x[k] > pivot);             // (valid keys are > 0)
+        inserted += __popc(mask);
+        while (mask) {
+          const int from = __ffs(mask) - 1;
+          mask &= mask - 1u;
+          const unsigned long long c = __shfl_sync(0xffffffffu, x[k], from);
+          // every key below c moves one place down (the last one falls off), c takes the place that opens
+          unsigned long long left = __shfl_up_sync(0xffffffffu, r[3], 1);
+          if (lane == 0) left = ~0ull;
+#pragma unroll
+          for (int i = 3; i >= 0; --i) {
+            const unsigned long long l = i == 0 ? left : r[i - 1];
+            r[i] = r[i] > c ? r[i] : (l > c ? c : l);
+          }
+        }
+      }
+      if (inserted) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[4 * lane + i] = r[i];
+        __syncwarp();
+        stored = min(stored + inserted, kFastPad);
+      }
+    }
+  }
+  return stored;
 }
 
 // Rank-merge of `nl` sorted lists (lists[l * kFastPad ..], cnt[l] valid keys each) into top[0..K): a key's rank = its

@@ -28,3 +28,12 @@ print("CTA start us: min 0 median %.1f max %.1f ; end us: min %.1f median %.1f m
 for rank in range(4):
     r = d[rank::4]
     print("rank", rank, "  ".join("%s %.0f" % (n, r[:, i].median()) for i, n in enumerate(names[:7])), " total %.0f" % (t[rank::4, 7] - t[rank::4, 0]).median())
+
+import numpy as np
+tot = (t[:, 7] - t[:, 0]).numpy() / 1e3
+srt = d[:, 1].numpy() / 1e3
+img_end = ((t[:, 7] - t0).view(-1, 4).max(dim=1).values / 1e3).numpy()
+for name, v in (("CTA total us", tot), ("check+sort us", srt), ("image end us", img_end)):
+    print(name, " ".join("p%d %.1f" % (q, np.percentile(v, q)) for q in (10, 50, 75, 90, 99, 100)))
+slow = srt.reshape(-1, 4).max(axis=1) > 1.5 * np.median(srt)
+print("images with a slow sort: %.1f %%; their end: median %.1f vs others %.1f" % (100 * slow.mean(), np.median(img_end[slow]) if slow.any() else 0, np.median(img_end[~slow])))
