@@ -261,24 +261,37 @@ def run_b200(args, w_job):
 
     K, Cv = w["K"], w["kpt"]
 
+    if args.gather == "auto":
+        # measured at 8 GPUs: rows stored by the kernel itself are a 20 MB burst at its end (+27 us on a 127 us step);
+        # moved by the copy engines they overlap the next batch completely, at the price of n-1 copy calls per step on the host --
+        # which smaller batches cannot hide (strong scaling, measured: 128 images per rank 106 us with the copies vs 84 us with the
+        # stores; 32 images per rank 128 us vs 68 us)
+        args.gather = "ce" if B * K * PackedDetections.WORDS * 4 >= (2 << 20) else "p2p"
+
     def setup_gather():
         """Gather buffers of the two result slots.  Preferred: symmetric memory (every rank's buffer mapped into every process)
         -- the select + post kernel then stores the wire rows straight into all ranks' buffers (rtm3d_decode_fused_gather) and
         the only other cross-GPU operation of a step is a barrier on the gather stream.  Else: rtm3d_pack_wire + NCCL all-gather."""
         per = K * PackedDetections.WORDS + 1
-        go = dict(stream=torch.cuda.Stream(device=dev), gathered=[None, None], mode="nccl", peers=[None, None], hdl=None)
-        if args.gather == "p2p" and Cv and not w.get("reg"):
+        go = dict(stream=torch.cuda.Stream(device=dev), gathered=[None, None], mode="nccl", peers=[None, None], hdl=None, n_slots=2)
+        if args.gather in ("p2p", "p2pd", "ce") and Cv and not w.get("reg"):
             try:
                 import ctypes
                 import torch.distributed._symmetric_memory as symm_mem
-                slot_words = world * B * per + world           # rows of every rank + one arrival flag per source rank
-                buf = symm_mem.empty((2, slot_words), dtype=torch.int32, device=dev)
+                # deferred pushes (p2pd): a batch's rows travel during the NEXT step, its flags arrive a step later -> one more slot
+                n_slots = 3 if args.gather == "p2pd" else 2
+                slot_words = (world * B * per + world + 3) // 4 * 4     # rows of every rank + one arrival flag per source rank (16-byte slots)
+                buf = symm_mem.empty((n_slots, slot_words), dtype=torch.int32, device=dev)
                 hdl = symm_mem.rendezvous(buf, dist.group.WORLD.group_name)
-                for slot in range(2):
-                    go["peers"][slot] = (ctypes.c_void_p * world)(*[int(ptr) + slot * slot_words * 4 for ptr in hdl.buffer_ptrs])
+                go["peers"] = [(ctypes.c_void_p * world)(*[int(ptr) + slot * slot_words * 4 for ptr in hdl.buffer_ptrs]) for slot in range(n_slots)]
                 buf.zero_()
-                go.update(mode="p2p", hdl=hdl, buf=buf, full=[buf[s_][:world * B * per].view(world * B, per) for s_ in range(2)],
-                          mine=[None, None], step_id=0)
+                go.update(mode=args.gather, hdl=hdl, buf=buf, full=[buf[s_][:world * B * per].view(world * B, per) for s_ in range(n_slots)],
+                          mine=[None] * n_slots, step_id=0, n_slots=n_slots, gathered=[None] * n_slots)
+                if args.gather == "ce":
+                    # copy engines: this rank's rows of a slot, as seen in every rank's buffer (peer-mapped views of the same offsets)
+                    go["wait_stream"] = torch.cuda.Stream(device=dev)
+                    go["peer_rows"] = [[hdl.get_buffer(r, (n_slots, slot_words), torch.int32)[s_][rank * B * per:(rank + 1) * B * per]
+                                        for r in range(world)] for s_ in range(n_slots)]
                 torch.cuda.synchronize()
                 dist.barrier()
                 return go
@@ -292,7 +305,7 @@ def run_b200(args, w_job):
     # N > 1 with the NCCL all-gather: its kernel runs beside the next batch's decode; the persistent scan kernel leaves it a
     # few SMs instead of queueing its last CTAs behind it (--max-ctas; 0 = one CTA per SM).  The fused peer-to-peer gather
     # has no second kernel to make room for.
-    max_ctas = args.max_ctas if args.max_ctas >= 0 else (0 if (world == 1 or gather_out["mode"] == "p2p") else 144)
+    max_ctas = args.max_ctas if args.max_ctas >= 0 else (0 if (world == 1 or gather_out["mode"] != "nccl") else 144)
     # result buffers are reused from call to call (saves ~35 us of host time per step); at N > 1 two decoders alternate so
     # that a batch's results stay untouched while the gather stream packs them
     mk_dec = lambda: HeatmapDecoder(THRESH, K, DOWN, max_ctas=max_ctas, reuse_outputs=True)
@@ -341,10 +354,15 @@ def run_b200(args, w_job):
         then a barrier of the ranks on a second stream), or rtm3d_pack_wire + NCCL all-gather on the second stream -- either
         way behind an event, so that the exchange of batch i overlaps the decode of batch i+1; the timed region ends with a
         device-wide synchronise, i.e. with every exchange complete."""
-        slot = i & 1
-        p2p = world > 1 and gather_out["mode"] == "p2p"
+        p2p = world > 1 and gather_out["mode"] in ("p2p", "p2pd", "ce")
+        deferred = world > 1 and gather_out["mode"] == "p2pd"
+        ce = world > 1 and gather_out["mode"] == "ce"
+        n_slots = gather_out["n_slots"] if world > 1 else 2
+        # p2p: the slot follows the batch counter (the id carried by the arrival flags); NCCL: the step index
+        slot = (gather_out["step_id"] % n_slots) if (p2p and marks is None) else (i & 1)
         if world > 1 and not capturing and gather_out["gathered"][slot] is not None:
-            torch.cuda.current_stream().wait_event(gather_out["gathered"][slot])    # batch i-2's rows have been exchanged
+            torch.cuda.current_stream().wait_event(gather_out["gathered"][slot])    # the batch that used this slot last has been exchanged
+        wait_slot, wait_id = slot, 0
         if graph is not None:
             graph.replay()
             det = None
@@ -352,7 +370,18 @@ def run_b200(args, w_job):
             gt = None
             if p2p and marks is None:
                 gather_out["step_id"] += 1
-                gt = (gather_out["peers"][slot], world, rank, gather_out["step_id"])
+                sid = gather_out["step_id"]
+                if deferred:
+                    prev_slot = (sid - 2) % n_slots
+                    gt = (gather_out["peers"][slot], gather_out["peers"][prev_slot] if sid > 1 else None, world, rank, sid - 1)
+                    wait_slot, wait_id = prev_slot, sid - 1                          # (what this launch delivers: the previous batch)
+                elif ce:
+                    gt = (gather_out["peers"][slot], None, world, rank, 0)              # the rows stay in this rank's buffer
+                    wait_id = sid
+                else:
+                    gt = (gather_out["peers"][slot], world, rank, sid)
+                    wait_id = sid
+                gather_out["last"] = (slot, sid)
             det = decode(i, decs_dev[i % len(decs_dev)], inputs if inputs is not None else sets[i % nsets], marks, gather=gt)
             if world > 1 and not p2p:
                 det.to_wire(gather_out["mine"][slot])                                 # one launch of the library (rtm3d_pack_wire)
@@ -361,16 +390,40 @@ def run_b200(args, w_job):
             ready.record()
             with torch.cuda.stream(gather_out["stream"]):
                 gather_out["stream"].wait_event(ready)
-                if p2p:
-                    if marks is None:                                               # every rank's rows of this batch have landed here
-                        _native.check(_native.lib().rtm3d_wait_gather(gather_out["buf"][slot].data_ptr(), B, K, 8, world, gather_out["step_id"],
+                if ce and marks is None and wait_id > 0:
+                    # the copy engines carry the rows to the other ranks (7 cudaMemcpyAsync over NVLink, no SM involved), the flag
+                    # follows in stream order; the wait for everybody's flags sits on a third stream
+                    mine_rows = gather_out["peer_rows"][slot][rank]
+                    for r in range(world):
+                        if r != rank:
+                            gather_out["peer_rows"][slot][r].copy_(mine_rows, non_blocking=True)
+                    _native.check(_native.lib().rtm3d_signal_gather(gather_out["peers"][slot], world, rank, B, K, 8, wait_id,
+                                                                    gather_out["stream"].cuda_stream), "rtm3d_signal_gather")
+                    with torch.cuda.stream(gather_out["wait_stream"]):
+                        _native.check(_native.lib().rtm3d_wait_gather(gather_out["buf"][wait_slot].data_ptr(), B, K, 8, world, wait_id,
+                                                                      gather_out["wait_stream"].cuda_stream), "rtm3d_wait_gather")
+                        done = torch.cuda.Event()
+                        done.record()
+                    gather_out["stream"].wait_event(done)
+                elif p2p:
+                    if marks is None and wait_id > 0:                                # every rank's rows of that batch have landed here
+                        _native.check(_native.lib().rtm3d_wait_gather(gather_out["buf"][wait_slot].data_ptr(), B, K, 8, world, wait_id,
                                                                       gather_out["stream"].cuda_stream), "rtm3d_wait_gather")
                 else:
                     dist.all_gather_into_tensor(gather_out["full"][slot], gather_out["mine"][slot])
-                if gather_out["gathered"][slot] is None:
-                    gather_out["gathered"][slot] = torch.cuda.Event()
-                gather_out["gathered"][slot].record()
+                if gather_out["gathered"][wait_slot] is None:
+                    gather_out["gathered"][wait_slot] = torch.cuda.Event()
+                gather_out["gathered"][wait_slot].record()
         return det
+
+    def flush_gather():
+        """Deferred peer-to-peer gather: the last batch's rows are still on their rank -- push them (rtm3d_push_gather) and wait
+        for every rank's.  Part of the timed region."""
+        if world > 1 and gather_out["mode"] == "p2pd" and gather_out.get("last"):
+            slot, sid = gather_out["last"]
+            st = torch.cuda.current_stream()
+            _native.check(_native.lib().rtm3d_push_gather(gather_out["peers"][slot], world, rank, B, K, 8, sid, st.cuda_stream), "rtm3d_push_gather")
+            _native.check(_native.lib().rtm3d_wait_gather(gather_out["buf"][slot].data_ptr(), B, K, 8, world, sid, st.cuda_stream), "rtm3d_wait_gather")
 
     def barrier():
         if world > 1:
@@ -410,7 +463,7 @@ def run_b200(args, w_job):
             torch.cuda.synchronize()
 
     # ---- timed region: exactly K steps, CUDA events on the launching stream, per-kernel marks on the same stream
-    p2p_mode = world > 1 and gather_out["mode"] == "p2p"
+    p2p_mode = world > 1 and gather_out["mode"] in ("p2p", "p2pd", "ce")
     marks = [] if (graphs is None and not p2p_mode) else None      # (p2p: ONE fused call per step; kernel times from a separate short run)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
@@ -420,6 +473,11 @@ def run_b200(args, w_job):
             step(i, marks)
         else:
             step(i, graph=graphs[i & 1])
+    flush_gather()
+    if world > 1:                                     # the timed region ends with every exchange complete
+        for ev in gather_out["gathered"]:
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
     e1.record()
     barrier()
     t_wall1 = time.perf_counter()
@@ -455,8 +513,9 @@ def run_b200(args, w_job):
         for slot in range(2):
             # two more (eager) steps: this rank's own wire rows, packed by rtm3d_pack_wire, are the reference for its block
             det = step(slot)
+            flush_gather()
             barrier()
-            full = gather_out["full"][slot]
+            full = gather_out["full"][gather_out["last"][0] if p2p_mode else slot]
             mine = det.to_wire()
             ok &= bool(torch.equal(full[rank * B:(rank + 1) * B], mine))                  # my block is my own wire rows
             sums = full.reshape(world, -1).to(torch.int64).sum(dim=1)                      # checksum of every rank's block as I received it
@@ -605,7 +664,10 @@ def main():
     ap.add_argument("--graph", action="store_true", help="replay the steps from a CUDA graph (default at N > 1; launch-bound small batches at N = 1)")
     ap.add_argument("--no-graph", action="store_true", help="N > 1: eager steps instead of the graph replay")
     ap.add_argument("--verify", action="store_true", help="N > 1: check the all-gathered detections against every owner's rows")
-    ap.add_argument("--gather", choices=["p2p", "nccl"], default="p2p", help="N > 1: fused peer-to-peer gather (symmetric memory) or pack + NCCL all-gather")
+    ap.add_argument("--gather", choices=["auto", "p2p", "p2pd", "ce", "nccl"], default="auto",
+                    help="N > 1: auto = ce when a rank's rows are >= 2 MB per batch, else p2p.  Fused peer-to-peer gather (symmetric memory) -- p2pd: a batch's rows are pushed while the next batch is sorted, "
+                         "p2p: stored at the end of their own launch; ce: rows left on their rank by the kernel and moved by the copy engines "
+                         "on a second stream -- or pack + NCCL all-gather")
     ap.add_argument("--nccl-ctas", type=int, default=0, help="N > 1: cap the CTAs of NCCL's kernels (NCCL_MAX_CTAS; 0 = NCCL's choice)")
     ap.add_argument("--max-ctas", type=int, default=-1, help="CTAs of the scan kernel (-1: all SMs at N=1, 144 at N>1)")
     args = ap.parse_args()

@@ -220,6 +220,32 @@ int rtm3d_decode_fused_gather(const void* hm, const void* off, const void* off2,
  * (wrap-safe comparison; bounded wait): behind it the batch of every rank can be read.  Step ids must increase.
  */
 int rtm3d_wait_gather(const void* wire, int B, int K, int n_vert, int n_peers, unsigned step_id, void* stream);
+/*
+ * Deferred variant of the fused gather, for a stream of batches over two (or more) slots of the gather buffers.  The rows of
+ * a batch leave a rank at the END of its select + post kernel; stored to n_peers ranks there they are one burst over NVLink
+ * that nothing overlaps (measured at 8 GPUs: +31 us on a 127 us step).  Here the launch stores its rows into THIS rank's
+ * buffer only (peer_wire[rank]) and, at its START, pushes the rows of the previous batch -- read back from
+ * peer_wire_prev[rank] -- into peer_wire_prev[r] of every other rank: posted stores that drain while the kernel sorts.  At
+ * its end it raises the PREVIOUS batch's arrival flag (prev_step_id) in every rank's peer_wire_prev buffer.  peer_wire_prev
+ * NULL (or prev_step_id 0): nothing to push (first batch).  The gather buffers must be symmetric (same 16-byte phase).
+ * rtm3d_push_gather flushes the last batch: its rows from peer_wire[rank] to the other ranks (one small kernel), then its
+ * flag (a second launch).  rtm3d_wait_gather is unchanged.
+ */
+int rtm3d_decode_fused_gather_deferred(const void* hm, const void* off, const void* off2, const void* kpt_hm, const void* voff2, int dtype,
+                                       int B, int C, int Cv, int H, int W, int n_vert, int K, float thresh, float down,
+                                       int64_t* cls, float* score, float* proj, float* verts, float* bbox, int32_t* flat, int32_t* counts,
+                                       float* kscore, float* kxy, int32_t* kflat, float* kpt_proj, float* kpt_score, int32_t* kpt_j,
+                                       float* verts_cv, void* ws, size_t ws_bytes, unsigned flags,
+                                       void* const* peer_wire, void* const* peer_wire_prev, int n_peers, int rank, unsigned prev_step_id,
+                                       void* stream);
+int rtm3d_push_gather(void* const* peer_wire, int n_peers, int rank, int B, int K, int n_vert, unsigned step_id, void* stream);
+/*
+ * The arrival flag alone: stores step_id into word [rank] of every gather buffer's flag array (one tiny kernel).  For callers
+ * that move the rows themselves -- e.g. with the copy engines (cudaMemcpyAsync to the peer-mapped buffers on a second stream,
+ * behind rtm3d_decode_fused_gather_deferred with peer_wire_prev = NULL, which leaves the rows in this rank's buffer): stream
+ * order puts the flag behind the copies, and no SM time or load/store bandwidth of the decode kernels is spent on NVLink.
+ */
+int rtm3d_signal_gather(void* const* peer_wire, int n_peers, int rank, int B, int K, int n_vert, unsigned step_id, void* stream);
 
 /*
  * Second half of rtm3d_decode_fused when it was called with RTM3D_FLAG_NO_SELECT (it then stops after the scan kernel, whose

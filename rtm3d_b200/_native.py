@@ -43,6 +43,10 @@ SIGNATURES = {
     "rtm3d_decode_fused_gather": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f,
                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _u, _vp, _i, _i, _u, _vp],
     "rtm3d_wait_gather": [_vp, _i, _i, _i, _i, _u, _vp],
+    "rtm3d_decode_fused_gather_deferred": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f,
+                                           _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _u, _vp, _vp, _i, _i, _u, _vp],
+    "rtm3d_push_gather": [_vp, _i, _i, _i, _i, _i, _u, _vp],
+    "rtm3d_signal_gather": [_vp, _i, _i, _i, _i, _i, _u, _vp],
     "rtm3d_epilogue_main": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp],
     "rtm3d_epilogue_keypoints": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "rtm3d_decode_fused_host": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _vp,

@@ -78,7 +78,7 @@ int launch_epilogues(const rtm3d::PlaneParams& q, int dtype, unsigned flags, cud
 // Plane-resident scan kernel + selection: writes score / flat / counts (C > 0) and kscore / kflat (Cv > 0).
 // Returns -1000 when the shape is not eligible for the scan kernel (the caller falls back).
 // post: when given (rtm3d_decode_fused), the selection and everything after it run in ONE kernel behind the scan kernel.
-struct GatherTarget { void* const* peers; int n_peers, rank; uint32_t step_id; size_t flag_offset; };
+struct GatherTarget { void* const* peers; int n_peers, rank; uint32_t step_id; size_t flag_offset; int deferred; void* const* prev_peers; uint32_t prev_step; };
 int scan_and_select(const rtm3d::PlaneParams& q, const rtm3d::WorkspaceLayout& L, void* ws, int dtype, unsigned flags, cudaStream_t s,
                     const rtm3d::PostFusedParams* post = nullptr, const GatherTarget* gt = nullptr) {
   unsigned char* base = static_cast<unsigned char*>(ws);
@@ -109,12 +109,17 @@ int scan_and_select(const rtm3d::PlaneParams& q, const rtm3d::WorkspaceLayout& L
   if (int e = cuda_fail(rc, "decode (scan kernel) launch")) return e;
   if (flags & RTM3D_FLAG_NO_SELECT) return 0;                       // the caller continues with rtm3d_select_post (bench.py's marks)
   if (post) {
-    rtm3d::SelectPostParams f{sp.cand, sp.cand_count, Sp, cap, q.thresh, q.score, q.flat, q.counts, q.kscore, q.kflat, *post, sp.stats, {}, 0, 0, 0u, 0, nullptr};
+    rtm3d::SelectPostParams f{sp.cand, sp.cand_count, Sp, cap, q.thresh, q.score, q.flat, q.counts, q.kscore, q.kflat, *post, sp.stats, {}, 0, 0, 0u, 0, nullptr, 0, {}, 0u};
     if (gt) {
       for (int r = 0; r < gt->n_peers; ++r) f.wire_peers[r] = static_cast<int32_t*>(gt->peers[r]);
       f.n_peers = gt->n_peers; f.wire_rank = gt->rank;
       f.step_id = gt->step_id; f.flag_offset = gt->flag_offset;
       f.done_counter = reinterpret_cast<uint32_t*>(base + L.queue_off + 64);
+      f.deferred = gt->deferred;
+      if (gt->deferred && gt->prev_peers && gt->prev_step != 0u) {
+        for (int r = 0; r < gt->n_peers; ++r) f.push_peers[r] = static_cast<int32_t*>(gt->prev_peers[r]);
+        f.push_step = gt->prev_step;
+      }
     }
     return cuda_fail(rtm3d::launch_select_post(f, dtype, s), "decode (select + post kernel) launch");
   }
@@ -440,9 +445,55 @@ int rtm3d_decode_fused_gather(const void* hm, const void* off, const void* off2,
   for (int r = 0; r < n_peers; ++r)
     if (!peer_wire[r] || reinterpret_cast<uintptr_t>(peer_wire[r]) % 4) return fail(RTM3D_ERR_NULL, "peer_wire[%d] is NULL or misaligned", r);
   // the arrival flags live behind the rows: word n_peers*B*(K*(9+2V)+1) of every gather buffer, one word per source rank
-  const GatherTarget gt{peer_wire, n_peers, rank, step_id, static_cast<size_t>(n_peers) * B * (static_cast<size_t>(K) * (9 + 2 * n_vert) + 1)};
+  const GatherTarget gt{peer_wire, n_peers, rank, step_id, static_cast<size_t>(n_peers) * B * (static_cast<size_t>(K) * (9 + 2 * n_vert) + 1), 0, nullptr, 0u};
   return decode_fused_impl(hm, off, off2, kpt_hm, voff2, dtype, B, C, Cv, H, W, n_vert, K, thresh, down, cls, score, proj, verts, bbox, flat,
                            counts, kscore, kxy, kflat, kpt_proj, kpt_score, kpt_j, verts_cv, ws, ws_bytes, flags, stream, &gt);
+}
+
+int rtm3d_decode_fused_gather_deferred(const void* hm, const void* off, const void* off2, const void* kpt_hm, const void* voff2, int dtype,
+                                       int B, int C, int Cv, int H, int W, int n_vert, int K, float thresh, float down, int64_t* cls,
+                                       float* score, float* proj, float* verts, float* bbox, int32_t* flat, int32_t* counts,
+                                       float* kscore, float* kxy, int32_t* kflat, float* kpt_proj, float* kpt_score, int32_t* kpt_j,
+                                       float* verts_cv, void* ws, size_t ws_bytes, unsigned flags, void* const* peer_wire,
+                                       void* const* peer_wire_prev, int n_peers, int rank, unsigned prev_step_id, void* stream) {
+  if (!peer_wire || n_peers < 1 || n_peers > 8 || rank < 0 || rank >= n_peers) return fail(RTM3D_ERR_SHAPE, "bad gather target (1..8 peers)");
+  for (int r = 0; r < n_peers; ++r) {
+    if (!peer_wire[r] || reinterpret_cast<uintptr_t>(peer_wire[r]) % 4) return fail(RTM3D_ERR_NULL, "peer_wire[%d] is NULL or misaligned", r);
+    if (peer_wire_prev && (!peer_wire_prev[r] || reinterpret_cast<uintptr_t>(peer_wire_prev[r]) % 4))
+      return fail(RTM3D_ERR_NULL, "peer_wire_prev[%d] is NULL or misaligned", r);
+    // the 16-byte body of a pushed block must be aligned at both ends: symmetric buffers share their low address bits
+    if (peer_wire_prev && (reinterpret_cast<uintptr_t>(peer_wire_prev[r]) & 15u) != (reinterpret_cast<uintptr_t>(peer_wire_prev[rank]) & 15u))
+      return fail(RTM3D_ERR_ALIGN, "gather buffers are not symmetric (different 16-byte phase)");
+  }
+  const GatherTarget gt{peer_wire, n_peers, rank, 0u, static_cast<size_t>(n_peers) * B * (static_cast<size_t>(K) * (9 + 2 * n_vert) + 1), 1,
+                        peer_wire_prev, peer_wire_prev ? prev_step_id : 0u};
+  return decode_fused_impl(hm, off, off2, kpt_hm, voff2, dtype, B, C, Cv, H, W, n_vert, K, thresh, down, cls, score, proj, verts, bbox, flat,
+                           counts, kscore, kxy, kflat, kpt_proj, kpt_score, kpt_j, verts_cv, ws, ws_bytes, flags, stream, &gt);
+}
+
+int rtm3d_push_gather(void* const* peer_wire, int n_peers, int rank, int B, int K, int n_vert, unsigned step_id, void* stream) {
+  if (!peer_wire || n_peers < 1 || n_peers > 8 || rank < 0 || rank >= n_peers || B < 1 || K < 1 || n_vert < 0) return fail(RTM3D_ERR_SHAPE, "bad gather target");
+  int32_t* peers[8] = {};
+  for (int r = 0; r < n_peers; ++r) {
+    if (!peer_wire[r] || reinterpret_cast<uintptr_t>(peer_wire[r]) % 4) return fail(RTM3D_ERR_NULL, "peer_wire[%d] is NULL or misaligned", r);
+    if ((reinterpret_cast<uintptr_t>(peer_wire[r]) & 15u) != (reinterpret_cast<uintptr_t>(peer_wire[rank]) & 15u))
+      return fail(RTM3D_ERR_ALIGN, "gather buffers are not symmetric (different 16-byte phase)");
+    peers[r] = static_cast<int32_t*>(peer_wire[r]);
+  }
+  const size_t flag_offset = static_cast<size_t>(n_peers) * B * (static_cast<size_t>(K) * (9 + 2 * n_vert) + 1);
+  return cuda_fail(rtm3d::launch_push_rows(peers, n_peers, rank, B, K, n_vert, step_id, flag_offset, static_cast<cudaStream_t>(stream)),
+                   "push_gather launch");
+}
+
+int rtm3d_signal_gather(void* const* peer_wire, int n_peers, int rank, int B, int K, int n_vert, unsigned step_id, void* stream) {
+  if (!peer_wire || n_peers < 1 || n_peers > 8 || rank < 0 || rank >= n_peers || B < 1 || K < 1 || n_vert < 0) return fail(RTM3D_ERR_SHAPE, "bad gather target");
+  int32_t* peers[8] = {};
+  for (int r = 0; r < n_peers; ++r) {
+    if (!peer_wire[r] || reinterpret_cast<uintptr_t>(peer_wire[r]) % 4) return fail(RTM3D_ERR_NULL, "peer_wire[%d] is NULL or misaligned", r);
+    peers[r] = static_cast<int32_t*>(peer_wire[r]);
+  }
+  const size_t flag_offset = static_cast<size_t>(n_peers) * B * (static_cast<size_t>(K) * (9 + 2 * n_vert) + 1);
+  return cuda_fail(rtm3d::launch_push_flag(peers, n_peers, rank, step_id, flag_offset, static_cast<cudaStream_t>(stream)), "signal_gather launch");
 }
 
 int rtm3d_wait_gather(const void* wire, int B, int K, int n_vert, int n_peers, unsigned step_id, void* stream) {
@@ -528,7 +579,7 @@ int rtm3d_select_post(const void* off, const void* off2, const void* voff2, int 
 #else
                             nullptr
 #endif
-                            , {}, 0, 0, 0u, 0, nullptr};
+                            , {}, 0, 0, 0u, 0, nullptr, 0, {}, 0u};
   return cuda_fail(rtm3d::launch_select_post(q, dtype, static_cast<cudaStream_t>(stream)), "select + post kernel launch");
 }
 

@@ -282,6 +282,32 @@ template <> __device__ __forceinline__ float gather_ld<__nv_bfloat16>(const __nv
   return __uint_as_float(static_cast<uint32_t>(u) << 16);
 }
 
+// Words [s0, s0 + n_words) of this rank's gather buffer to the same place in every other rank's buffer.  The buffers are
+// symmetric (same offsets, same base alignment): source and destination share their low address bits, so the 16-byte body is
+// aligned at both ends.  All NT threads of the block; stores are posted (nobody waits for them here).
+template <int NT>
+__device__ __forceinline__ void push_words(int32_t* const* peers, int n_peers, int self, size_t s0, int n_words) {
+  const int32_t* src = peers[self] + s0;
+  const int to16 = static_cast<int>(((16u - (reinterpret_cast<uintptr_t>(src) & 15u)) & 15u) >> 2);
+  const int head = to16 < n_words ? to16 : n_words;
+  const int body4 = (n_words - head) >> 2;
+  const int tail0 = head + body4 * 4;
+  const int tid = threadIdx.x;
+  if (tid < head) {
+    const int32_t v = src[tid];
+    for (int r = 0; r < n_peers; ++r) if (r != self) peers[r][s0 + tid] = v;
+  }
+  for (int q4 = tid; q4 < body4; q4 += NT) {
+    const int i = head + q4 * 4;
+    const int4 v = *reinterpret_cast<const int4*>(src + i);
+    for (int r = 0; r < n_peers; ++r) if (r != self) *reinterpret_cast<int4*>(peers[r] + s0 + i) = v;
+  }
+  if (tid < n_words - tail0) {
+    const int32_t v = src[tail0 + tid];
+    for (int r = 0; r < n_peers; ++r) if (r != self) peers[r][s0 + tail0 + tid] = v;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Fused select + post kernel of rtm3d_decode_fused behind the scan kernel.  A cluster of four CTAs per image:
 //   (S) the image's selection problems are sorted by different CTAs at the same time -- CTA 0: the main problem (its C*Sp
@@ -333,6 +359,18 @@ __global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kSpThreads,
     peer_count[r] = cluster.map_shared_rank(&s_count, r);
   }
   SP_MARK(0);
+  if (sp.push_step != 0u) {
+    // deferred gather: the previous batch's rows of this CTA's block (and, by the image's first CTA, its count word) go to the
+    // other ranks now; they drain over NVLink while this kernel sorts
+    const int words_ = 9 + 2 * V;
+    const size_t per_img_ = static_cast<size_t>(K) * words_ + 1;
+    const size_t img0_ = (static_cast<size_t>(sp.wire_rank) * p.B + b) * per_img_;
+    push_words<kSpThreads>(sp.push_peers, sp.n_peers, sp.wire_rank, img0_ + static_cast<size_t>(n0) * words_, max(0, n1 - n0) * words_);
+    if (rank == 0 && tid == 0) {
+      const int32_t c = sp.push_peers[sp.wire_rank][img0_ + static_cast<size_t>(K) * words_];
+      for (int r = 0; r < sp.n_peers; ++r) if (r != sp.wire_rank) sp.push_peers[r][img0_ + static_cast<size_t>(K) * words_] = c;
+    }
+  }
   cluster.sync();          // every CTA of the cluster has started: its shared memory may be written by its peers from here on
   SP_MARK(1);
 
@@ -629,6 +667,7 @@ __global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kSpThreads,
     // (16-byte stores for the aligned body of the CTA's block of rows, scalar head and tail: remote stores are packets)
     const size_t s0 = img0 + static_cast<size_t>(n0) * words;
     for (int r = 0; r < sp.n_peers; ++r) {
+      if (sp.deferred && r != sp.wire_rank) continue;                // (the others get these rows at the start of the next launch)
       int32_t* dst = sp.wire_peers[r] + s0;
       const int to16 = static_cast<int>(((16u - (reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u) >> 2);   // words up to the next 16-byte boundary
       const int head = to16 < n_words ? to16 : n_words;
@@ -642,7 +681,8 @@ __global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kSpThreads,
       if (tid < n_words - tail0) dst[tail0 + tid] = s_wire[tail0 + tid];
       if (rank == 0 && tid == 0) sp.wire_peers[r][img0 + static_cast<size_t>(K) * words] = n_det;
     }
-    if (sp.step_id != 0u) {
+    const uint32_t flag_step = sp.deferred ? sp.push_step : sp.step_id;      // (deferred: the batch pushed at the start)
+    if (flag_step != 0u) {
       // arrival flag: every CTA makes its remote stores visible system-wide and counts itself; the last one of the launch
       // then tells every peer that ALL rows of this rank's batch have landed (release pattern: rows, fence, flag)
       __syncthreads();
@@ -653,8 +693,8 @@ __global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kSpThreads,
           *sp.done_counter = 0u;                                     // clean for the next launch
           __threadfence_system();
           for (int r = 0; r < sp.n_peers; ++r) {
-            volatile uint32_t* fl = reinterpret_cast<volatile uint32_t*>(sp.wire_peers[r] + sp.flag_offset);
-            fl[sp.wire_rank] = sp.step_id;
+            volatile uint32_t* fl = reinterpret_cast<volatile uint32_t*>((sp.deferred ? sp.push_peers[r] : sp.wire_peers[r]) + sp.flag_offset);
+            fl[sp.wire_rank] = flag_step;
           }
         }
       }
@@ -948,6 +988,37 @@ __global__ void wait_flags_kernel(const uint32_t* flags, int n, uint32_t value) 
   }
   __threadfence_system();
 }
+// Flush of the deferred gather (behind the last batch): the rows, then -- in a second launch, i.e. with every store of the
+// first one complete -- the arrival flag.
+struct PushPeers { int32_t* p[8]; };
+__global__ void __launch_bounds__(128) push_rows_kernel(PushPeers peers, int n_peers, int rank, int B, int K, int words) {
+  const int b = blockIdx.x / kPostSplit, q = blockIdx.x % kPostSplit;
+  const int per = (K + kPostSplit - 1) / kPostSplit, n0 = q * per, n1 = min(K, n0 + per);
+  const size_t per_img = static_cast<size_t>(K) * words + 1;
+  const size_t img0 = (static_cast<size_t>(rank) * B + b) * per_img;
+  // (the image's last block takes the count word along)
+  const int n_words = max(0, n1 - n0) * words + (q == kPostSplit - 1 ? 1 : 0);
+  const size_t s0 = q == kPostSplit - 1 && n1 <= n0 ? img0 + static_cast<size_t>(K) * words : img0 + static_cast<size_t>(n0) * words;
+  push_words<128>(peers.p, n_peers, rank, s0, n_words);
+}
+__global__ void push_flag_kernel(PushPeers peers, int n_peers, int rank, size_t flag_offset, uint32_t step_id) {
+  if (threadIdx.x < n_peers) reinterpret_cast<volatile uint32_t*>(peers.p[threadIdx.x] + flag_offset)[rank] = step_id;
+}
+int launch_push_rows(int32_t* const* peers, int n_peers, int rank, int B, int K, int n_vert, uint32_t step_id, size_t flag_offset, cudaStream_t s) {
+  PushPeers pp{};
+  for (int r = 0; r < n_peers; ++r) pp.p[r] = peers[r];
+  push_rows_kernel<<<static_cast<unsigned>(B) * kPostSplit, 128, 0, s>>>(pp, n_peers, rank, B, K, 9 + 2 * n_vert);
+  push_flag_kernel<<<1, 32, 0, s>>>(pp, n_peers, rank, flag_offset, step_id);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_push_flag(int32_t* const* peers, int n_peers, int rank, uint32_t step_id, size_t flag_offset, cudaStream_t s) {
+  PushPeers pp{};
+  for (int r = 0; r < n_peers; ++r) pp.p[r] = peers[r];
+  push_flag_kernel<<<1, 32, 0, s>>>(pp, n_peers, rank, flag_offset, step_id);
+  return static_cast<int>(cudaGetLastError());
+}
+
 int launch_wait_flags(const uint32_t* flags, int n, uint32_t value, cudaStream_t s) {
   wait_flags_kernel<<<1, 1, 0, s>>>(flags, n, value);
   return static_cast<int>(cudaGetLastError());

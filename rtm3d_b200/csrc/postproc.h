@@ -65,6 +65,13 @@ struct SelectPostParams {
   uint32_t step_id;
   size_t flag_offset;
   uint32_t* done_counter;      // workspace word, 0 between launches
+  // deferred gather (rtm3d_decode_fused_gather_deferred): this launch stores its rows into THIS rank's buffer only and, at its
+  // start, pushes the rows of the previous batch (push_peers = the previous batch's slot of every gather buffer) to the other
+  // ranks -- posted stores that drain while the kernel sorts, instead of a burst at its end; the arrival flag it raises at
+  // its end is the previous batch's (push_step; 0 = nothing to push)
+  int deferred;
+  int32_t* push_peers[8];
+  uint32_t push_step;
 };
 // Batched 3D-box fit behind the decoder (boxfit.cu; utils/model_utils.py:264-312).
 struct BoxFitParams {
@@ -99,6 +106,9 @@ int launch_encode_targets(const TargetParams& p, cudaStream_t s);
 int launch_focal_loss(const float* logits, const float* target, size_t n, float alpha, float beta, double* acc, float* loss, cudaStream_t s);
 int launch_focal_grad(const float* logits, const float* target, size_t n, float alpha, float beta, const double* acc, const float* upstream,
                       float* grad, cudaStream_t s);
+// flush of the deferred gather: the rows of one batch from this rank's buffer to the other ranks, then its arrival flag
+int launch_push_rows(int32_t* const* peers, int n_peers, int rank, int B, int K, int n_vert, uint32_t step_id, size_t flag_offset, cudaStream_t s);
+int launch_push_flag(int32_t* const* peers, int n_peers, int rank, uint32_t step_id, size_t flag_offset, cudaStream_t s);
 int launch_wait_flags(const uint32_t* flags, int n, uint32_t value, cudaStream_t s);
 size_t select_post_smem(int Cv, int K, int n_vert);
 int launch_select_post(const SelectPostParams& p, int dtype, cudaStream_t s);

@@ -282,7 +282,10 @@ class HeatmapDecoder:
         fused call is then issued as selection-only ``rtm3d_decode_fused`` + ``rtm3d_post_fused``: the same two launches
         with an event in between).  ``gather`` = (ctypes array of peer-mapped gather buffers, n_peers, rank, step id of the arrival flag or 0): the wire rows
         of the detections are stored straight into every rank's gather buffer by the select + post kernel
-        (``rtm3d_decode_fused_gather``: the path's one exchange, fused; no pack kernel, no collective call)."""
+        (``rtm3d_decode_fused_gather``: the path's one exchange, fused; no pack kernel, no collective call).  A 5-tuple
+        (peers of this batch's slot, peers of the previous batch's slot or None, n_peers, rank, id of the previous batch) selects
+        ``rtm3d_decode_fused_gather_deferred``: the rows stay on this rank and the previous batch's rows are pushed while this
+        launch sorts (flush the last batch with ``rtm3d_push_gather``)."""
         def mark():
             if marks is not None:
                 e = torch.cuda.Event(enable_timing=True)
@@ -332,15 +335,21 @@ class HeatmapDecoder:
             if gather is not None:
                 if marks is not None:
                     raise ValueError("gather and marks cannot be combined (the fused gather is one call)")
-                peers, n_peers, rank, step_id = gather
-                rc = self._lib.rtm3d_decode_fused_gather(
-                    main.data_ptr(), off.data_ptr(), off2.data_ptr(), kpt_logits.data_ptr(), voff2.data_ptr(), dt,
-                    B, C, Cv, H, W, V, K, self.score_thresh, self.down_sample,
-                    det.cls.data_ptr(), det.score.data_ptr(), det.proj.data_ptr(), det.verts.data_ptr(), det.bbox.data_ptr(),
-                    det.flat.data_ptr(), det.counts.data_ptr(), cand.score.data_ptr(), cand.xy.data_ptr(), cand.flat.data_ptr(),
-                    grp.kpt_proj.data_ptr(), grp.kpt_score.data_ptr(), grp.kpt_j.data_ptr(), grp.verts.data_ptr(),
-                    ws.data_ptr(), ws.numel(), self.flags, peers, n_peers, rank, step_id, stream)
-                _native.check(rc, "rtm3d_decode_fused_gather")
+                outs = (det.cls.data_ptr(), det.score.data_ptr(), det.proj.data_ptr(), det.verts.data_ptr(), det.bbox.data_ptr(),
+                        det.flat.data_ptr(), det.counts.data_ptr(), cand.score.data_ptr(), cand.xy.data_ptr(), cand.flat.data_ptr(),
+                        grp.kpt_proj.data_ptr(), grp.kpt_score.data_ptr(), grp.kpt_j.data_ptr(), grp.verts.data_ptr())
+                ins = (main.data_ptr(), off.data_ptr(), off2.data_ptr(), kpt_logits.data_ptr(), voff2.data_ptr(), dt,
+                       B, C, Cv, H, W, V, K, self.score_thresh, self.down_sample)
+                if len(gather) == 4:
+                    peers, n_peers, rank, step_id = gather
+                    rc = self._lib.rtm3d_decode_fused_gather(*ins, *outs, ws.data_ptr(), ws.numel(), self.flags, peers, n_peers, rank, step_id, stream)
+                    _native.check(rc, "rtm3d_decode_fused_gather")
+                else:
+                    # deferred: (this batch's slot of every gather buffer, the previous batch's slot or None, n_peers, rank, id of the previous batch)
+                    peers, prev_peers, n_peers, rank, prev_step_id = gather
+                    rc = self._lib.rtm3d_decode_fused_gather_deferred(*ins, *outs, ws.data_ptr(), ws.numel(), self.flags, peers, prev_peers, n_peers,
+                                                                     rank, prev_step_id, stream)
+                    _native.check(rc, "rtm3d_decode_fused_gather_deferred")
                 return det, cand, grp
             mark()
             legacy = bool(self.flags & (_native.FLAG_LEGACY_PLANES | _native.FLAG_FORCE_GENERIC))

@@ -60,3 +60,49 @@ def test_fused_gather_rows_equal_pack_wire(shape, n_peers):
     for p in range(n_peers):
         mask[1 + p * (words + 3): 1 + p * (words + 3) + words] = False
     assert bool((arena[mask] == -1).all()), "stores outside the gather buffers"
+
+
+@pytest.mark.parametrize("n_peers", [2, 3])
+def test_deferred_gather_pushes_previous_batch(n_peers):
+    """rtm3d_decode_fused_gather_deferred over two slots and three batches: a launch keeps its rows on its own rank and pushes
+    the previous batch; rtm3d_push_gather flushes the last one.  Afterwards every rank holds every rank's rows of the last
+    two batches, and the flags carry their ids."""
+    B, H, W, K = 3, 48, 160, 30
+    dev = torch.device("cuda:0")
+    w = dict(B=B, C=3, H=H, W=W, K=K, kpt=9)
+    per = _rows(B, K)
+    words = n_peers * B * per + n_peers
+    slot_words = (words + 3) // 4 * 4 + 4                         # the same 16-byte phase for every slot and rank, as symmetric memory gives
+    bufs = [torch.full((2 * slot_words + 4,), -1, dtype=torch.int32, device=dev) for _ in range(n_peers)]
+    base = [b[(16 - b.data_ptr() % 16) % 16 // 4 + 1:] for b in bufs]          # deliberately 4 bytes past a 16-byte boundary
+    slots = [[base[r][s * slot_words: s * slot_words + words] for s in range(2)] for r in range(n_peers)]
+    for r in range(n_peers):
+        for s_ in range(2):
+            slots[r][s_][n_peers * B * per:] = 0
+    peers = [(ctypes.c_void_p * n_peers)(*[slots[r][s_].data_ptr() for r in range(n_peers)]) for s_ in range(2)]
+    decs = [HeatmapDecoder(0.4, K, 4.0) for _ in range(n_peers)]
+    lib = _native.lib()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    want = {}
+    n_steps = 3
+    for step in range(n_steps):
+        for rank in range(n_peers):
+            logits, kpt, _ = bench.make_inputs(torch, w, dev, 500 + 10 * step + rank, kind="trained" if (step + rank) % 2 else "randn")
+            prev = peers[(step - 1) & 1] if step > 0 else None
+            det, _, _ = decs[rank].decode_with_keypoints(logits, kpt, gather=(peers[step & 1], prev, n_peers, rank, step))    # id of batch s = s + 1
+            want[(step, rank)] = det.to_wire().clone()
+    for rank in range(n_peers):
+        _native.check(lib.rtm3d_push_gather(peers[(n_steps - 1) & 1], n_peers, rank, B, K, 8, n_steps, stream), "rtm3d_push_gather")
+    for r in range(n_peers):
+        for step in (n_steps - 2, n_steps - 1):
+            _native.check(lib.rtm3d_wait_gather(slots[r][step & 1].data_ptr(), B, K, 8, n_peers, step + 1, stream), "rtm3d_wait_gather")
+    torch.cuda.synchronize()
+    for step in (n_steps - 2, n_steps - 1):
+        full = torch.cat([want[(step, rank)] for rank in range(n_peers)], dim=0)
+        counts = full[:, -1]
+        valid = (torch.arange(K, device=dev)[None, :] < counts[:, None]).repeat_interleave(PackedDetections.WORDS, dim=1)
+        for r in range(n_peers):
+            got = slots[r][step & 1][:n_peers * B * per].view(n_peers * B, per)
+            assert torch.equal(got[:, -1], counts), f"rank {r} batch {step}: counts"
+            assert torch.equal(got[:, :-1][valid], full[:, :-1][valid]), f"rank {r} batch {step}: rows"
+            assert torch.equal(slots[r][step & 1][n_peers * B * per:], torch.full((n_peers,), step + 1, dtype=torch.int32, device=dev)), "flags"
