@@ -318,9 +318,14 @@ def run_b200(args, w_job):
         names = ["scan+select(main)", "box3d"]
     elif Cv:
         names = ["scan_planes(main+kpt)", "select_post"]
+        probe = []
+        decs_dev[0].decode_with_keypoints(sets[0][0], sets[0][1], marks=probe)      # which kernels serve this shape
+        torch.cuda.synchronize()
+        if decs_dev[0].staged_path == "legacy":                   # planes larger than the scan kernel's ring (cfg5): round-1 kernels
+            names = ["decode_planes(main+kpt; round-1 streaming kernel)", "post_fused"]
     else:
         names = ["scan+select+epilogue(main)"]
-    launches_per_step = {"scan_planes(main+kpt)": 1, "select_post": 1, "scan+select(main)": 2, "box3d": 1, "scan+select+epilogue(main)": 3}
+    launches_per_step = {"scan_planes(main+kpt)": 1, "select_post": 1, "decode_planes(main+kpt; round-1 streaming kernel)": 1, "post_fused": 1, "scan+select(main)": 2, "box3d": 1, "scan+select+epilogue(main)": 3}
     n_launches = sum(launches_per_step[n] for n in names)       # (+ the wire-packing kernel when the gather goes through NCCL: added below)
 
     capturing = False

@@ -136,6 +136,9 @@ class HeatmapDecoder:
         # work of a small batch
         self.reuse_outputs = bool(reuse_outputs)
         self._out = {}
+        # which kernels the staged (marks) form of decode_with_keypoints used last: "scan" (scan kernel + select/post kernel) or
+        # "legacy" (round-1 plane-streaming kernel + post kernel: planes that do not fit the scan kernel's ring)
+        self.staged_path = "legacy" if legacy else "scan"
 
     # ------------------------------------------------------------------ workspace
     def _workspace(self, device, B, C, H, W):
@@ -368,6 +371,7 @@ class HeatmapDecoder:
             if marks is not None and not legacy and rc == _native.ERR_SHAPE:
                 # the scan kernel does not serve this shape (planes larger than its ring): the round-1 kernels in two stages
                 legacy = True
+                self.staged_path = "legacy"
                 rc = self._lib.rtm3d_decode_fused(
                     main.data_ptr(), off.data_ptr(), off2.data_ptr(), kpt_logits.data_ptr(), voff2.data_ptr(), dt,
                     B, C, Cv, H, W, V, K, self.score_thresh, self.down_sample,
