@@ -3,6 +3,7 @@
 #pragma once
 #include "common.cuh"
 #include "params.h"
+#include "tier_math.cuh"
 
 namespace rtm3d {
 
@@ -55,10 +56,10 @@ static __device__ __noinline__ void block_emit_main(const DecodeParams& p, int b
         ox = to_f32(off[static_cast<size_t>(2 * v) * HW + rem]);
         oy = to_f32(off[static_cast<size_t>(2 * v + 1) * HW + rem]);
       }
-      mx = __fadd_rn(static_cast<float>(xi), sigmoid_ref(r0));
-      my = __fadd_rn(static_cast<float>(yi), sigmoid_ref(r1));
-      vx = __fmul_rn(p.down, __fadd_rn(ox, mx));
-      vy = __fmul_rn(p.down, __fadd_rn(oy, my));
+      mx = subpixel(xi, r0);
+      my = subpixel(yi, r1);
+      vx = regress_coord(p.down, ox, mx);
+      vy = regress_coord(p.down, oy, my);
     }
     float lo_x = (valid && vert) ? vx : INFINITY, hi_x = (valid && vert) ? vx : -INFINITY;
     float lo_y = (valid && vert) ? vy : INFINITY, hi_y = (valid && vert) ? vy : -INFINITY;
@@ -77,8 +78,8 @@ static __device__ __noinline__ void block_emit_main(const DecodeParams& p, int b
     if (v == 0) {
       p.cls[row] = valid ? c : -1;
       p.score[row] = valid ? key_score(key) : 0.f;
-      p.proj[row * 2 + 0] = valid ? __fmul_rn(p.down, mx) : 0.f;
-      p.proj[row * 2 + 1] = valid ? __fmul_rn(p.down, my) : 0.f;
+      p.proj[row * 2 + 0] = valid ? scale_coord(p.down, mx) : 0.f;
+      p.proj[row * 2 + 1] = valid ? scale_coord(p.down, my) : 0.f;
       p.bbox[row * 4 + 0] = valid ? lo_x : 0.f;
       p.bbox[row * 4 + 1] = valid ? lo_y : 0.f;
       p.bbox[row * 4 + 2] = valid ? hi_x : 0.f;
@@ -100,8 +101,8 @@ __device__ __forceinline__ void emit_kpt_row(const DecodeParams& p, int b, int c
   const float r1 = to_f32(off2[HW + flat]);
   const size_t row = (static_cast<size_t>(b) * p.C + c) * p.K + j;
   p.kscore[row] = score;
-  p.kxy[row * 2 + 0] = __fadd_rn(static_cast<float>(xi), sigmoid_ref(r0));
-  p.kxy[row * 2 + 1] = __fadd_rn(static_cast<float>(yi), sigmoid_ref(r1));
+  p.kxy[row * 2 + 0] = subpixel(xi, r0);
+  p.kxy[row * 2 + 1] = subpixel(yi, r1);
   p.kflat[row] = static_cast<int32_t>(flat);
 }
 

@@ -3,6 +3,7 @@
 #include "params.h"
 #include "../../include/rtm3d_decode.h"
 #include "postproc.h"
+#include "tier_math.cuh"
 #include "select_common.cuh"
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
@@ -41,10 +42,10 @@ __global__ void __launch_bounds__(256) epilogue_main_kernel(const EpiMainParams 
       ox = to_f32(off[static_cast<size_t>(2 * v) * HW + rem]);
       oy = to_f32(off[static_cast<size_t>(2 * v + 1) * HW + rem]);
     }
-    mx = __fadd_rn(static_cast<float>(xi), sigmoid_ref(r0));
-    my = __fadd_rn(static_cast<float>(yi), sigmoid_ref(r1));
-    vx = __fmul_rn(p.down, __fadd_rn(ox, mx));
-    vy = __fmul_rn(p.down, __fadd_rn(oy, my));
+    mx = subpixel(xi, r0);
+    my = subpixel(yi, r1);
+    vx = regress_coord(p.down, ox, mx);
+    vy = regress_coord(p.down, oy, my);
   }
   float lo_x = (valid && vert) ? vx : INFINITY, hi_x = (valid && vert) ? vx : -INFINITY;
   float lo_y = (valid && vert) ? vy : INFINITY, hi_y = (valid && vert) ? vy : -INFINITY;
@@ -62,8 +63,8 @@ __global__ void __launch_bounds__(256) epilogue_main_kernel(const EpiMainParams 
   }
   if (v == 0) {
     p.cls[row] = c;
-    p.proj[row * 2 + 0] = valid ? __fmul_rn(p.down, mx) : 0.f;
-    p.proj[row * 2 + 1] = valid ? __fmul_rn(p.down, my) : 0.f;
+    p.proj[row * 2 + 0] = valid ? scale_coord(p.down, mx) : 0.f;
+    p.proj[row * 2 + 1] = valid ? scale_coord(p.down, my) : 0.f;
     p.bbox[row * 4 + 0] = valid ? lo_x : 0.f;
     p.bbox[row * 4 + 1] = valid ? lo_y : 0.f;
     p.bbox[row * 4 + 2] = valid ? hi_x : 0.f;
@@ -95,8 +96,8 @@ __global__ void __launch_bounds__(256) epilogue_kpt_kernel(const EpiKptParams p)
   const T* off2 = reinterpret_cast<const T*>(p.voff2) + static_cast<size_t>(b) * 2 * HW;
   const float r0 = to_f32(off2[flat]);
   const float r1 = to_f32(off2[HW + flat]);
-  p.kxy[row * 2 + 0] = __fadd_rn(static_cast<float>(xi), sigmoid_ref(r0));
-  p.kxy[row * 2 + 1] = __fadd_rn(static_cast<float>(yi), sigmoid_ref(r1));
+  p.kxy[row * 2 + 0] = subpixel(xi, r0);
+  p.kxy[row * 2 + 1] = subpixel(yi, r1);
 }
 
 int launch_epilogue_kpt(const EpiKptParams& p, int dtype, cudaStream_t s) {
@@ -113,19 +114,6 @@ int launch_epilogue_kpt(const EpiKptParams& p, int dtype, cudaStream_t s) {
 // search of _group_vertexs_kf, (3) per detection: 2D box, class, centre.  Arithmetic and association order are those of
 // epilogue_main_kernel, epilogue_kpt_kernel and group_vertices_kernel (bit-identical results).
 constexpr int kPostThreads = 256;
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-  return static_cast<unsigned long long>(__float_as_uint(lo)) | (static_cast<unsigned long long>(__float_as_uint(hi)) << 32);
-}
-__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
-  unsigned long long d;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
-  unsigned long long d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
 // A cluster of four CTAs per image, each with a quarter of the detections: small CTAs spread evenly over the SMs and a
 // CTA's (detection, channel) pairs fit one round of its threads.  Every CTA needs all of the image's candidates: each
 // computes a quarter and stores it into the shared memory of all four (distributed shared memory).
@@ -156,8 +144,8 @@ __global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kPostThread
     const size_t row = static_cast<size_t>(b) * Cv * K + i;
     const int flat = p.kflat[row];
     const int yi = flat / p.W, xi = flat - yi * p.W;
-    const float x = __fadd_rn(static_cast<float>(xi), sigmoid_ref(to_f32(voff2[flat])));
-    const float y = __fadd_rn(static_cast<float>(yi), sigmoid_ref(to_f32(voff2[HW + flat])));
+    const float x = subpixel(xi, to_f32(voff2[flat]));
+    const float y = subpixel(yi, to_f32(voff2[HW + flat]));
     const int k = i / K, j = i - k * K;
 #pragma unroll
     for (int r = 0; r < kPostSplit; ++r) peer_xy[r][k * KP + j] = make_float2(x, y);
@@ -169,8 +157,8 @@ __global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kPostThread
     if (n < n_det) {
       const int rem = p.flat[static_cast<size_t>(b) * K + n] % HW;
       const int yi = rem / p.W, xi = rem - yi * p.W;
-      mx = __fadd_rn(static_cast<float>(xi), sigmoid_ref(to_f32(off2[rem])));
-      my = __fadd_rn(static_cast<float>(yi), sigmoid_ref(to_f32(off2[HW + rem])));
+      mx = subpixel(xi, to_f32(off2[rem]));
+      my = subpixel(yi, to_f32(off2[HW + rem]));
     }
     s_m[2 * (n - n0)] = mx; s_m[2 * (n - n0) + 1] = my;
   }
@@ -189,8 +177,8 @@ __global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kPostThread
         oy = to_f32(off[static_cast<size_t>(2 * k + 1) * HW + rem]);
       }
     }
-    const float vx = valid ? __fmul_rn(p.down, __fadd_rn(ox, mx)) : 0.f;
-    const float vy = valid ? __fmul_rn(p.down, __fadd_rn(oy, my)) : 0.f;
+    const float vx = valid ? regress_coord(p.down, ox, mx) : 0.f;
+    const float vy = valid ? regress_coord(p.down, oy, my) : 0.f;
     if (k < V) {
       s_v[(nl * V + k) * 2] = vx; s_v[(nl * V + k) * 2 + 1] = vy;
       float* vout = p.verts + ((static_cast<size_t>(b) * K + n) * V + k) * 2;
@@ -205,38 +193,9 @@ __global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kPostThread
         if (p.verts_cv) { p.verts_cv[row * 2] = 0.f; p.verts_cv[row * 2 + 1] = 0.f; }
       } else {
         const float* cand = s_xy + static_cast<size_t>(k) * KP * 2;
-        // (x, y) pairs go through the packed fp32x2 pipe (FADD2 / FMUL2: IEEE round-to-nearest per lane, the same
-        // results as the scalar ops, half the instructions).  Four independent (best, index) chains over j = 4i + u keep
-        // the compare/select dependency off the critical path; merged with torch.argmin's first-minimal-index rule.
-        const unsigned long long* cand2 = reinterpret_cast<const unsigned long long*>(cand);
-        const unsigned long long m2 = pack2(mx, my), o2 = pack2(ox, oy);
-        auto dist = [&](int j) {
-          const unsigned long long df = sub2(sub2(cand2[j], m2), o2);      // (v - m) - off      (models/model.py:147,149)
-          const unsigned long long sq = mul2(df, df);
-          return __fadd_rn(__uint_as_float(static_cast<uint32_t>(sq)), __uint_as_float(static_cast<uint32_t>(sq >> 32)));
-        };
-        float bd[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
-        int bi[4] = {0, 0, 0, 0};
-        int j = 0;
-#pragma unroll 2
-        for (; j + 4 <= K; j += 4) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float d = dist(j + u);
-            if (d < bd[u]) { bd[u] = d; bi[u] = j + u; }
-          }
-        }
-        for (; j < K; ++j) {
-          const float d = dist(j);
-          if (d < bd[0]) { bd[0] = d; bi[0] = j; }      // (j is past every index chain 0 has seen)
-        }
-        float best = bd[0];
-        int bj = bi[0];
-#pragma unroll
-        for (int u = 1; u < 4; ++u)
-          if (bd[u] < best || (bd[u] == best && bi[u] < bj)) { best = bd[u]; bj = bi[u]; }
-        p.kpt_proj[row * 2] = __fmul_rn(p.down, cand[2 * bj]);
-        p.kpt_proj[row * 2 + 1] = __fmul_rn(p.down, cand[2 * bj + 1]);
+        const int bj = nearest_candidate(cand, K, mx, my, ox, oy);
+        p.kpt_proj[row * 2] = scale_coord(p.down, cand[2 * bj]);
+        p.kpt_proj[row * 2 + 1] = scale_coord(p.down, cand[2 * bj + 1]);
         p.kpt_score[row] = p.kscore[(static_cast<size_t>(b) * Cv + k) * K + bj];
         p.kpt_j[row] = bj;
         if (p.verts_cv) { p.verts_cv[row * 2] = vx; p.verts_cv[row * 2 + 1] = vy; }
@@ -261,8 +220,8 @@ __global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kPostThread
       }
     }
     p.cls[row] = c;
-    p.proj[row * 2] = valid ? __fmul_rn(p.down, s_m[2 * nl]) : 0.f;
-    p.proj[row * 2 + 1] = valid ? __fmul_rn(p.down, s_m[2 * nl + 1]) : 0.f;
+    p.proj[row * 2] = valid ? scale_coord(p.down, s_m[2 * nl]) : 0.f;
+    p.proj[row * 2 + 1] = valid ? scale_coord(p.down, s_m[2 * nl + 1]) : 0.f;
     p.bbox[row * 4 + 0] = lo_x; p.bbox[row * 4 + 1] = lo_y; p.bbox[row * 4 + 2] = hi_x; p.bbox[row * 4 + 3] = hi_y;
   }
 }
@@ -426,8 +385,8 @@ __global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kSpThreads,
       if (valid) {
         const int rem = fl % HW;
         const int yi = rem / p.W, xi = rem - yi * p.W;
-        dt.mx = __fadd_rn(static_cast<float>(xi), sigmoid_ref(gather_ld<T>(off2 + rem)));
-        dt.my = __fadd_rn(static_cast<float>(yi), sigmoid_ref(gather_ld<T>(off2 + HW + rem)));
+        dt.mx = subpixel(xi, gather_ld<T>(off2 + rem));
+        dt.my = subpixel(yi, gather_ld<T>(off2 + HW + rem));
       }
 #pragma unroll
       for (int r = 0; r < kPostSplit; ++r) peer_det[r][j] = dt;
@@ -456,8 +415,8 @@ __global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kSpThreads,
     sp.kscore[row] = j < have ? key_score(top[j]) : 0.0f;
     sp.kflat[row] = fl;
     const int yi = fl / p.W, xi = fl - yi * p.W;
-    const float x = __fadd_rn(static_cast<float>(xi), sigmoid_ref(gather_ld<T>(voff2 + fl)));
-    const float y = __fadd_rn(static_cast<float>(yi), sigmoid_ref(gather_ld<T>(voff2 + HW + fl)));
+    const float x = subpixel(xi, gather_ld<T>(voff2 + fl));
+    const float y = subpixel(yi, gather_ld<T>(voff2 + HW + fl));
 #pragma unroll
     for (int r = 0; r < kPostSplit; ++r) peer_xy[r][kc * KP + j] = make_float2(x, y);
     p.kxy[row * 2] = x; p.kxy[row * 2 + 1] = y;
@@ -502,8 +461,8 @@ __global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kSpThreads,
           sp.kscore[row] = sc[u];
           sp.kflat[row] = fl[u];
           const int yi = fl[u] / p.W, xi = fl[u] - yi * p.W;
-          const float x = __fadd_rn(static_cast<float>(xi), sigmoid_ref(gx[u]));
-          const float y = __fadd_rn(static_cast<float>(yi), sigmoid_ref(gy[u]));
+          const float x = subpixel(xi, gx[u]);
+          const float y = subpixel(yi, gy[u]);
 #pragma unroll
           for (int r = 0; r < kPostSplit; ++r) peer_xy[r][kc * KP + j] = make_float2(x, y);
           p.kxy[row * 2] = x; p.kxy[row * 2 + 1] = y;
@@ -567,8 +526,8 @@ __global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kSpThreads,
         }
       }
     }
-    const float vx = valid ? __fmul_rn(p.down, __fadd_rn(ox, mx)) : 0.f;
-    const float vy = valid ? __fmul_rn(p.down, __fadd_rn(oy, my)) : 0.f;
+    const float vx = valid ? regress_coord(p.down, ox, mx) : 0.f;
+    const float vy = valid ? regress_coord(p.down, oy, my) : 0.f;
     if (k < V) {
       s_v[(nl * V + k) * 2] = vx; s_v[(nl * V + k) * 2 + 1] = vy;
       float* vout = p.verts + ((static_cast<size_t>(b) * K + n) * V + k) * 2;
@@ -583,38 +542,9 @@ __global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kSpThreads,
         if (p.verts_cv) { p.verts_cv[row * 2] = 0.f; p.verts_cv[row * 2 + 1] = 0.f; }
       } else {
         const float* cand = s_xy + static_cast<size_t>(k) * KP * 2;
-        // (x, y) pairs go through the packed fp32x2 pipe (IEEE round-to-nearest per lane, the same results as the scalar
-        // ops, half the instructions).  Four independent (best, index) chains over j = 4i + u keep the compare/select
-        // dependency off the critical path; merged with torch.argmin's first-minimal-index rule.
-        const unsigned long long* cand2 = reinterpret_cast<const unsigned long long*>(cand);
-        const unsigned long long m2 = pack2(mx, my), o2 = pack2(ox, oy);
-        auto dist = [&](int j) {
-          const unsigned long long df = sub2(sub2(cand2[j], m2), o2);      // (v - m) - off      (models/model.py:147,149)
-          const unsigned long long sq = mul2(df, df);
-          return __fadd_rn(__uint_as_float(static_cast<uint32_t>(sq)), __uint_as_float(static_cast<uint32_t>(sq >> 32)));
-        };
-        float bd[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
-        int bi[4] = {0, 0, 0, 0};
-        int j = 0;
-#pragma unroll 2
-        for (; j + 4 <= K; j += 4) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float dd = dist(j + u);
-            if (dd < bd[u]) { bd[u] = dd; bi[u] = j + u; }
-          }
-        }
-        for (; j < K; ++j) {
-          const float dd = dist(j);
-          if (dd < bd[0]) { bd[0] = dd; bi[0] = j; }      // (j is past every index chain 0 has seen)
-        }
-        float best = bd[0];
-        int bj = bi[0];
-#pragma unroll
-        for (int u = 1; u < 4; ++u)
-          if (bd[u] < best || (bd[u] == best && bi[u] < bj)) { best = bd[u]; bj = bi[u]; }
-        p.kpt_proj[row * 2] = __fmul_rn(p.down, cand[2 * bj]);
-        p.kpt_proj[row * 2 + 1] = __fmul_rn(p.down, cand[2 * bj + 1]);
+        const int bj = nearest_candidate(cand, K, mx, my, ox, oy);
+        p.kpt_proj[row * 2] = scale_coord(p.down, cand[2 * bj]);
+        p.kpt_proj[row * 2 + 1] = scale_coord(p.down, cand[2 * bj + 1]);
         p.kpt_score[row] = sp.kscore[(static_cast<size_t>(b) * Cv + k) * K + bj];
         p.kpt_j[row] = bj;
         if (p.verts_cv) { p.verts_cv[row * 2] = vx; p.verts_cv[row * 2 + 1] = vy; }
@@ -641,7 +571,7 @@ __global__ void __cluster_dims__(kPostSplit, 1, 1) __launch_bounds__(kSpThreads,
         lo_y = fminf(lo_y, vy); hi_y = fmaxf(hi_y, vy);
       }
     }
-    const float px = valid ? __fmul_rn(p.down, s_det[n].mx) : 0.f, py = valid ? __fmul_rn(p.down, s_det[n].my) : 0.f;
+    const float px = valid ? scale_coord(p.down, s_det[n].mx) : 0.f, py = valid ? scale_coord(p.down, s_det[n].my) : 0.f;
     p.cls[row] = c;
     p.proj[row * 2] = px;
     p.proj[row * 2 + 1] = py;
@@ -797,29 +727,22 @@ __global__ void __launch_bounds__(256) group_vertices_kernel(const GroupParams p
     const int flat = p.flat[static_cast<size_t>(b) * K + n];
     const int rem = flat % HW;
     const int yi = rem / p.W, xi = rem - yi * p.W;
-    const float mx = __fadd_rn(static_cast<float>(xi), sigmoid_ref(to_f32(off2[rem])));
-    const float my = __fadd_rn(static_cast<float>(yi), sigmoid_ref(to_f32(off2[HW + rem])));
+    const float mx = subpixel(xi, to_f32(off2[rem]));
+    const float my = subpixel(yi, to_f32(off2[HW + rem]));
     float ox = 0.f, oy = 0.f;
     if (k < p.n_vert) {
       ox = to_f32(off[static_cast<size_t>(2 * k) * HW + rem]);
       oy = to_f32(off[static_cast<size_t>(2 * k + 1) * HW + rem]);
     }
     const float* cand = s_xy + static_cast<size_t>(k) * K * 2;
-    float best = INFINITY;
-    int bj = 0;
-    for (int j = 0; j < K; ++j) {
-      const float dx = __fsub_rn(__fsub_rn(cand[2 * j], mx), ox);
-      const float dy = __fsub_rn(__fsub_rn(cand[2 * j + 1], my), oy);
-      const float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-      if (d < best) { best = d; bj = j; }
-    }
-    p.kpt_proj[row * 2] = __fmul_rn(p.down, cand[2 * bj]);
-    p.kpt_proj[row * 2 + 1] = __fmul_rn(p.down, cand[2 * bj + 1]);
+    const int bj = nearest_candidate(cand, K, mx, my, ox, oy);
+    p.kpt_proj[row * 2] = scale_coord(p.down, cand[2 * bj]);
+    p.kpt_proj[row * 2 + 1] = scale_coord(p.down, cand[2 * bj + 1]);
     p.kpt_score[row] = kscore[static_cast<size_t>(k) * K + bj];
     p.kpt_j[row] = bj;
     if (p.verts_cv) {
-      p.verts_cv[row * 2] = __fmul_rn(p.down, __fadd_rn(ox, mx));
-      p.verts_cv[row * 2 + 1] = __fmul_rn(p.down, __fadd_rn(oy, my));
+      p.verts_cv[row * 2] = regress_coord(p.down, ox, mx);
+      p.verts_cv[row * 2 + 1] = regress_coord(p.down, oy, my);
     }
   }
 }
