@@ -331,6 +331,22 @@ int rtm3d_focal_loss_grad(const float* logits, const float* target, size_t n, fl
                           const float* upstream, float* grad, void* stream);
 
 /*
+ * The gather-L1 losses of RTM3DLoss.__call__ (models/rtm3d_loss.py:302-330: offset-from-main, vertex offset, main offset):
+ * per entry e the channels c0[e], c0[e]+1 (c0 NULL: 0, 1) of the NCHW f32 map at (img[e], y[e], x[e]), through a sigmoid when
+ * `sigmoid` != 0 (:319, :327), against target[e][0..1]; loss = mean |pred - target| over the entries with valid[e] != 0
+ * (F.l1_loss, reduction 'mean'; NaN when none is valid, as torch).  The reference permutes the whole map to NHWC first
+ * (:302, :316, :324: a full copy per loss); this reads the 2 n scalars.  acc: double[3] scratch (sum, elements, valid entries
+ * outside the map -- skipped, torch would raise), kept for the gradient call.
+ * rtm3d_gather_l1_loss_grad: grad f32 [B,C,H,W] = d(upstream * loss)/d map (zero-filled, then accumulated); upstream NULL = 1.
+ */
+int rtm3d_gather_l1_loss(const float* map, int B, int C, int H, int W, const int64_t* img, const int64_t* x, const int64_t* y,
+                         const int32_t* c0, const uint8_t* valid, const float* target, int n, int sigmoid, double* acc, float* loss,
+                         void* stream);
+int rtm3d_gather_l1_loss_grad(const float* map, int B, int C, int H, int W, const int64_t* img, const int64_t* x, const int64_t* y,
+                              const int32_t* c0, const uint8_t* valid, const float* target, int n, int sigmoid, const double* acc,
+                              const float* upstream, float* grad, void* stream);
+
+/*
  * Packs the Tier A result of a batch into the wire rows of the multi-GPU gather (the path's one collective):
  * wire int32 [B][K*(9+2*n_vert) + 1] = per image K rows of (cls | score | proj 2 | verts 2*n_vert | bbox 4 | flat) as
  * 32-bit patterns, then counts[b].  One launch instead of a chain of torch cat / cast kernels.

@@ -49,5 +49,49 @@ def main():
     print("wrote", path, "positives", int((m_hm == 1).sum()), "loss", float(loss), "empty", float(empty_loss))
 
 
+def reference_loss_class():
+    """The reference's RTM3DLoss; the modules it imports but __call__ never touches (albumentations transforms, the un-vendored
+    KITTI devkit) are stubbed."""
+    import types
+    sys.dont_write_bytecode = True
+    if ref_import.REF_ROOT not in sys.path:
+        sys.path.insert(0, ref_import.REF_ROOT)
+    for name in ("preprocess", "preprocess.transforms", "datasets", "datasets.data", "datasets.data.kitti", "datasets.data.kitti.devkit_object",
+                 "datasets.data.kitti.devkit_object.utils"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["preprocess.transforms"].ToAbsoluteCoords = lambda: None
+    sys.modules["datasets.data.kitti.devkit_object"].utils = sys.modules["datasets.data.kitti.devkit_object.utils"]
+    from models.rtm3d_loss import RTM3DLoss
+    from utils.ParamList import ParamList
+    return RTM3DLoss, ParamList
+
+
+def reference_loss(pred, fields, weights):
+    """(loss, parts, gradients w.r.t. the four logit maps) from the reference's RTM3DLoss.__call__."""
+    import types
+    RTM3DLoss, ParamList = reference_loss_class()
+    ns = types.SimpleNamespace
+    cfg = ns(MODEL=ns(FOCAL_LOSS_ALPHA=2.0, FOCAL_LOSS_BEDA=4.0),
+             DATASET=ns(GAUSSIAN_SIGMA_MAX=3., GAUSSIAN_SIGMA_MIN=1., BBOX_AREA_MAX=10., BBOX_AREA_MIN=1., VERTEX_OFFSET_INFER=[1.0]),
+             TRAINING=ns(W_MKF=weights[0], W_VKF=1.0, W_VFM=weights[1], W_M_OFF=weights[2], W_V_OFF=weights[3]))
+    t = ParamList((1, 1))
+    for k, v in fields.items():
+        t.add_field(k, v.clone())
+    leaves = [p.clone().requires_grad_(True) for p in pred]
+    loss, parts = RTM3DLoss(cfg)([x.clone() for x in leaves], t)        # (sigmoid_hm works in place: on the clones)
+    loss.backward()
+    return loss.detach(), parts, [x.grad for x in leaves]
+
+
+def main_loss():
+    pred, fields = train_ref.make_loss_case()
+    loss, parts, grads = reference_loss(pred, fields, train_ref.LOSS_WEIGHTS)
+    path = os.path.join(ROOT, "tests", "golden", "loss_golden.npz")
+    np.savez_compressed(path, parts=parts.numpy(), **{f"grad{i}": g.numpy() for i, g in enumerate(grads)})
+    print("wrote", path, "parts", parts.tolist())
+
+
 if __name__ == "__main__":
     main()
+    main_loss()

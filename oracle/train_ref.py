@@ -72,3 +72,57 @@ def focal_loss(logits: torch.Tensor, target: torch.Tensor, alpha=2.0, beta=4.0) 
     neg_loss = (torch.log(1 - pred) * torch.pow(pred, alpha) * neg_w * neg).sum()
     num = pos.sum()
     return -neg_loss if num == 0 else -(pos_loss + neg_loss) / num
+
+
+def rtm3d_loss(pred_logits, fields, weights, alpha=2.0, beta=4.0):
+    """models/rtm3d_loss.py:268-340 (RTM3DLoss.__call__) restated: focal loss on the main heat-map + the three gather-L1 losses.
+    ``fields``: dict of the targets' tensors; ``weights`` = (W_MKF, W_VFM, W_M_OFF, W_V_OFF).  Does not modify the logits.
+    Returns (loss, [main_kf, ver_coor, main_offset, vertex_offset, loss])."""
+    import torch.nn.functional as F
+    m_hm_pred, ver_coor_pred, m_off_pred, v_off_pred = pred_logits
+    m_projs, v_projs = fields["m_proj"].long(), fields["v_proj"].long()
+    img_id = fields["img_id"].long()
+    m_mask, not_noise = fields["mask"].bool(), fields["noise_mask"].bool().bitwise_not()
+    mask_3d, v_mask = fields["mask_3d"].bool(), fields["v_mask"].bool()
+    loss_main_kf = focal_loss(m_hm_pred, fields["m_hm"], alpha, beta)
+    num_vc = ver_coor_pred.shape[1] // 2
+    ofm_valid = m_mask & not_noise & mask_3d
+    ofm_valid_expand = v_mask[ofm_valid].view(-1)
+    vc = ver_coor_pred.permute(0, 2, 3, 1)[img_id[ofm_valid], m_projs[ofm_valid][:, 1], m_projs[ofm_valid][:, 0]].reshape(-1, 2)
+    loss_ver_coor = F.l1_loss(vc[ofm_valid_expand], fields["v_coor_off"][ofm_valid].view(-1, 2)[ofm_valid_expand], reduction="mean")
+    bs = img_id.view(-1, 1).repeat(1, num_vc).view(-1)
+    vp = v_projs.view(-1, 2)
+    ver_valid = ofm_valid.view(-1, 1).repeat(1, num_vc).view(-1) & v_mask.view(-1)
+    pos_v = v_off_pred.permute(0, 2, 3, 1)[bs[ver_valid], vp[ver_valid][:, 1], vp[ver_valid][:, 0]].sigmoid()
+    loss_vertex_offset = F.l1_loss(pos_v, fields["v_off"].view(-1, 2)[ver_valid], reduction="mean")
+    m_valid = m_mask & not_noise
+    pos_m = m_off_pred.permute(0, 2, 3, 1)[img_id[m_valid], m_projs[m_valid][:, 1], m_projs[m_valid][:, 0]].sigmoid()
+    loss_main_offset = F.l1_loss(pos_m, fields["m_off"][m_valid], reduction="mean")
+    w_mkf, w_vfm, w_moff, w_voff = weights
+    parts = [loss_main_kf * w_mkf, loss_ver_coor * w_vfm, loss_main_offset * w_moff, loss_vertex_offset * w_voff]
+    loss = parts[0] + parts[1] + parts[2] + parts[3]
+    return loss, parts + [loss]
+
+
+LOSS_FIELDS = ("m_hm", "m_proj", "m_off", "v_coor_off", "v_proj", "v_off", "img_id", "mask", "noise_mask", "mask_3d", "v_mask")
+LOSS_WEIGHTS = (1.0, 0.5, 1.0, 1.0)          # W_MKF, W_VFM, W_M_OFF, W_V_OFF of the golden case
+
+
+def make_loss_case(seed=3, B=3, C=3, H=24, W=40, N=19, V=8):
+    """Seeded logits + targets of the loss golden (shared by the generator and the live pin)."""
+    g = torch.Generator().manual_seed(seed)
+    pred = [torch.randn(B, C, H, W, generator=g) * 2 - 2, torch.randn(B, 2 * V, H, W, generator=g) * 3, torch.randn(B, 2, H, W, generator=g),
+            torch.randn(B, 2, H, W, generator=g)]
+    m_hm = torch.rand(B, C, H, W, generator=g) ** 6
+    m_proj = torch.stack([torch.randint(0, W, (N,), generator=g), torch.randint(0, H, (N,), generator=g)], 1)
+    m_proj[1] = m_proj[0]                                             # two objects on one pixel: their gradients add up
+    img_id = torch.randint(0, B, (N,), generator=g)
+    img_id[1] = img_id[0]
+    for i in range(N):
+        m_hm[img_id[i], i % C, m_proj[i, 1], m_proj[i, 0]] = 1.0
+    fields = dict(m_hm=m_hm, m_proj=m_proj, m_off=torch.rand(N, 2, generator=g), v_coor_off=torch.randn(N, V, 2, generator=g) * 5,
+                  v_proj=torch.stack([torch.randint(0, W, (N, V), generator=g), torch.randint(0, H, (N, V), generator=g)], 2),
+                  v_off=torch.rand(N, V, 2, generator=g), img_id=img_id, mask=(torch.rand(N, generator=g) > 0.15).float(),
+                  noise_mask=(torch.rand(N, generator=g) > 0.8).float(), mask_3d=(torch.rand(N, generator=g) > 0.1).float(),
+                  v_mask=torch.rand(N, V, generator=g) > 0.3)
+    return pred, fields

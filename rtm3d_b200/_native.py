@@ -58,6 +58,8 @@ SIGNATURES = {
     "rtm3d_group_vertices": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp],
     "rtm3d_fit_box3d": [_vp, _vp, _vp, _vp, _i, _vp, _i, _c.POINTER(_f), _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "rtm3d_encode_main_targets": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "rtm3d_gather_l1_loss": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
+    "rtm3d_gather_l1_loss_grad": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp],
     "rtm3d_focal_loss": [_vp, _vp, _sz, _f, _f, _vp, _vp, _vp],
     "rtm3d_focal_loss_grad": [_vp, _vp, _sz, _f, _f, _vp, _vp, _vp, _vp],
     "rtm3d_pack_wire": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],

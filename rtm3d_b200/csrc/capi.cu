@@ -660,6 +660,24 @@ int rtm3d_focal_loss_grad(const float* logits, const float* target, size_t n, fl
   return cuda_fail(rtm3d::launch_focal_grad(logits, target, n, alpha, beta, acc, upstream, grad, static_cast<cudaStream_t>(stream)), "focal_loss_grad launch");
 }
 
+int rtm3d_gather_l1_loss(const float* map, int B, int C, int H, int W, const int64_t* img, const int64_t* x, const int64_t* y,
+                         const int32_t* c0, const uint8_t* valid, const float* target, int n, int sigmoid, double* acc, float* loss,
+                         void* stream) {
+  if (!map || !acc || !loss || (n > 0 && (!img || !x || !y || !valid || !target))) return fail(RTM3D_ERR_NULL, "NULL pointer argument");
+  if (B < 1 || C < 2 || H < 1 || W < 1 || n < 0) return fail(RTM3D_ERR_SHAPE, "bad shape B=%d C=%d H=%d W=%d n=%d", B, C, H, W, n);
+  const rtm3d::GatherL1Params p{map, B, C, H, W, img, x, y, c0, valid, target, n, sigmoid ? 1 : 0, acc};
+  return cuda_fail(rtm3d::launch_gather_l1(p, loss, static_cast<cudaStream_t>(stream)), "gather_l1_loss launch");
+}
+
+int rtm3d_gather_l1_loss_grad(const float* map, int B, int C, int H, int W, const int64_t* img, const int64_t* x, const int64_t* y,
+                              const int32_t* c0, const uint8_t* valid, const float* target, int n, int sigmoid, const double* acc,
+                              const float* upstream, float* grad, void* stream) {
+  if (!map || !acc || !grad || (n > 0 && (!img || !x || !y || !valid || !target))) return fail(RTM3D_ERR_NULL, "NULL pointer argument");
+  if (B < 1 || C < 2 || H < 1 || W < 1 || n < 0) return fail(RTM3D_ERR_SHAPE, "bad shape B=%d C=%d H=%d W=%d n=%d", B, C, H, W, n);
+  const rtm3d::GatherL1Params p{map, B, C, H, W, img, x, y, c0, valid, target, n, sigmoid ? 1 : 0, const_cast<double*>(acc)};
+  return cuda_fail(rtm3d::launch_gather_l1_grad(p, upstream, grad, static_cast<cudaStream_t>(stream)), "gather_l1_loss_grad launch");
+}
+
 int rtm3d_pack_wire(const int64_t* cls, const float* score, const float* proj, const float* verts, const float* bbox,
                     const int32_t* flat, const int32_t* counts, int B, int K, int n_vert, int32_t* wire, void* stream) {
   if (!cls || !score || !proj || !verts || !bbox || !flat || !counts || !wire) return fail(RTM3D_ERR_NULL, "NULL pointer argument");

@@ -103,6 +103,15 @@ struct TargetParams {
   int32_t* radius;         // [N]
 };
 int launch_encode_targets(const TargetParams& p, cudaStream_t s);
+// gather-L1 losses (models/rtm3d_loss.py:302-330): see train_side.cu
+struct GatherL1Params {
+  const float* map; int B, C, H, W;
+  const int64_t* img; const int64_t* x; const int64_t* y; const int32_t* c0; const uint8_t* valid; const float* target;
+  int n, sigmoid;
+  double* acc;
+};
+int launch_gather_l1(const GatherL1Params& p, float* loss, cudaStream_t s);
+int launch_gather_l1_grad(const GatherL1Params& p, const float* upstream, float* grad, cudaStream_t s);
 int launch_focal_loss(const float* logits, const float* target, size_t n, float alpha, float beta, double* acc, float* loss, cudaStream_t s);
 int launch_focal_grad(const float* logits, const float* target, size_t n, float alpha, float beta, const double* acc, const float* upstream,
                       float* grad, cudaStream_t s);

@@ -145,4 +145,83 @@ int launch_focal_grad(const float* logits, const float* target, size_t n, float 
   return static_cast<int>(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The three gather-L1 losses of RTM3DLoss.__call__ (models/rtm3d_loss.py:302-330): two channels (c0, c0+1) of an NCHW map
+// gathered at (image, y, x) per entry, optional sigmoid, mean absolute error against a target pair over the valid entries.
+// The reference permutes the WHOLE map to NHWC (a full copy) before indexing it; here only the 2 n scalars are read.
+//   acc[0] = sum |pred - target|, acc[1] = number of elements (2 per valid entry), acc[2] = valid entries with (image, y, x)
+//   outside the map (skipped; torch would raise)
+__device__ __forceinline__ bool gather_l1_entry(const GatherL1Params& p, int e, size_t& idx, float& t0, float& t1) {
+  if (!p.valid[e]) return false;
+  const long long img = p.img[e], x = p.x[e], y = p.y[e];
+  const int c0 = p.c0 ? p.c0[e] : 0;
+  if (img < 0 || img >= p.B || x < 0 || x >= p.W || y < 0 || y >= p.H || c0 < 0 || c0 + 1 >= p.C) { idx = ~static_cast<size_t>(0); return true; }
+  idx = ((static_cast<size_t>(img) * p.C + c0) * p.H + static_cast<size_t>(y)) * p.W + static_cast<size_t>(x);
+  t0 = p.target[2 * static_cast<size_t>(e)]; t1 = p.target[2 * static_cast<size_t>(e) + 1];
+  return true;
+}
+__global__ void __launch_bounds__(256) gather_l1_reduce_kernel(const GatherL1Params p) {
+  double sum = 0.0, cnt = 0.0, bad = 0.0;
+  const size_t HW = static_cast<size_t>(p.H) * p.W;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < p.n; e += gridDim.x * blockDim.x) {
+    size_t idx; float t0 = 0.f, t1 = 0.f;
+    if (!gather_l1_entry(p, e, idx, t0, t1)) continue;
+    if (idx == ~static_cast<size_t>(0)) { bad += 1.0; continue; }
+    float p0 = p.map[idx], p1 = p.map[idx + HW];
+    if (p.sigmoid) { p0 = 1.0f / (1.0f + expf(-p0)); p1 = 1.0f / (1.0f + expf(-p1)); }
+    sum += static_cast<double>(fabsf(__fsub_rn(p0, t0))) + static_cast<double>(fabsf(__fsub_rn(p1, t1)));
+    cnt += 2.0;
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    bad += __shfl_xor_sync(0xffffffffu, bad, d);
+  }
+  __shared__ double sh[3][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sh[0][warp] = sum; sh[1][warp] = cnt; sh[2][warp] = bad; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double v = 0.0;
+    for (int w = 0; w < 8; ++w) v += sh[threadIdx.x][w];
+    if (v != 0.0) atomicAdd(&p.acc[threadIdx.x], v);
+  }
+}
+// F.l1_loss(..., reduction='mean'): sum / count (NaN for an empty selection, as torch)
+__global__ void gather_l1_finish_kernel(const double* acc, float* loss) { *loss = static_cast<float>(acc[0] / acc[1]); }
+
+// d loss / d map, accumulated (atomicAdd: several entries may share a pixel) into a zeroed gradient map
+__global__ void __launch_bounds__(256) gather_l1_grad_kernel(const GatherL1Params p, const float* upstream, float* grad) {
+  const size_t HW = static_cast<size_t>(p.H) * p.W;
+  const float scale = (upstream ? *upstream : 1.0f) / static_cast<float>(p.acc[1]);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < p.n; e += gridDim.x * blockDim.x) {
+    size_t idx; float t0 = 0.f, t1 = 0.f;
+    if (!gather_l1_entry(p, e, idx, t0, t1) || idx == ~static_cast<size_t>(0)) continue;
+    float p0 = p.map[idx], p1 = p.map[idx + HW], d0 = 1.f, d1 = 1.f;
+    if (p.sigmoid) {
+      p0 = 1.0f / (1.0f + expf(-p0)); p1 = 1.0f / (1.0f + expf(-p1));
+      d0 = p0 * (1.0f - p0); d1 = p1 * (1.0f - p1);
+    }
+    const float s0 = p0 > t0 ? 1.f : (p0 < t0 ? -1.f : 0.f), s1 = p1 > t1 ? 1.f : (p1 < t1 ? -1.f : 0.f);   // sign(pred - target)
+    if (s0 != 0.f) atomicAdd(grad + idx, scale * s0 * d0);
+    if (s1 != 0.f) atomicAdd(grad + idx + HW, scale * s1 * d1);
+  }
+}
+
+int launch_gather_l1(const GatherL1Params& p, float* loss, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(p.acc, 0, 3 * sizeof(double), s);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const int blocks = p.n > 0 ? (p.n + 255) / 256 : 1;
+  gather_l1_reduce_kernel<<<blocks < 1184 ? blocks : 1184, 256, 0, s>>>(p);
+  gather_l1_finish_kernel<<<1, 1, 0, s>>>(p.acc, loss);
+  return static_cast<int>(cudaGetLastError());
+}
+int launch_gather_l1_grad(const GatherL1Params& p, const float* upstream, float* grad, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(grad, 0, static_cast<size_t>(p.B) * p.C * p.H * p.W * sizeof(float), s);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const int blocks = p.n > 0 ? (p.n + 255) / 256 : 1;
+  gather_l1_grad_kernel<<<blocks < 1184 ? blocks : 1184, 256, 0, s>>>(p, upstream, grad);
+  return static_cast<int>(cudaGetLastError());
+}
+
 }  // namespace rtm3d

@@ -90,3 +90,72 @@ def test_gpu_focal_loss_and_gradient_match_goldens():
     ref.backward()
     assert np.isclose(float(loss.detach()), float(ref.detach()), rtol=2e-5)
     np.testing.assert_allclose(logits.grad.cpu().numpy() / 3.0, lg2.grad.cpu().numpy(), rtol=2e-4, atol=1e-8)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the whole loss: models/rtm3d_loss.py:268-340
+LOSS_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loss_golden.npz")
+
+
+def test_oracle_loss_matches_reference_goldens():
+    g = np.load(LOSS_GOLD)
+    pred, fields = train_ref.make_loss_case()
+    leaves = [p.clone().requires_grad_(True) for p in pred]
+    loss, parts = train_ref.rtm3d_loss(leaves, fields, train_ref.LOSS_WEIGHTS)
+    loss.backward()
+    np.testing.assert_allclose(np.array([float(x) for x in parts]), g["parts"], rtol=1e-6)
+    for i, leaf in enumerate(leaves):
+        np.testing.assert_allclose(leaf.grad.numpy(), g[f"grad{i}"], rtol=1e-5, atol=1e-9)
+    assert all(torch.equal(a, b.detach()) for a, b in zip(pred, leaves)), "the restatement must not modify the logits"
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference checkout not mounted")
+def test_loss_goldens_are_what_the_live_reference_yields():
+    from oracle import make_train_golden
+    g = np.load(LOSS_GOLD)
+    pred, fields = train_ref.make_loss_case()
+    loss, parts, grads = make_train_golden.reference_loss(pred, fields, train_ref.LOSS_WEIGHTS)
+    np.testing.assert_allclose(parts.numpy(), g["parts"], rtol=1e-6)
+    for i, gr in enumerate(grads):
+        np.testing.assert_allclose(gr.numpy(), g[f"grad{i}"], rtol=1e-6, atol=1e-10)
+
+
+@pytest.mark.gpu
+def test_gpu_rtm3d_loss_matches_reference_goldens():
+    import types
+    from rtm3d_b200 import RTM3DLoss
+    g = np.load(LOSS_GOLD)
+    dev = torch.device("cuda:0")
+    pred, fields = train_ref.make_loss_case()
+    leaves = [p.to(dev).clone().requires_grad_(True) for p in pred]
+    before = [p.detach().clone() for p in leaves]
+    ns = types.SimpleNamespace
+    W = train_ref.LOSS_WEIGHTS
+    cfg = ns(MODEL=ns(FOCAL_LOSS_ALPHA=2.0, FOCAL_LOSS_BEDA=4.0), TRAINING=ns(W_MKF=W[0], W_VFM=W[1], W_M_OFF=W[2], W_V_OFF=W[3]))
+    targets = types.SimpleNamespace(get_field=lambda k: fields[k])
+    loss, parts = RTM3DLoss(cfg)(leaves, targets)
+    loss.backward()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(parts.cpu().numpy(), g["parts"], rtol=2e-5)
+    for i, leaf in enumerate(leaves):
+        assert torch.equal(before[i], leaf.detach()), "the loss modified its inputs"
+        np.testing.assert_allclose(leaf.grad.cpu().numpy(), g[f"grad{i}"], rtol=2e-4, atol=2e-8, err_msg=f"gradient of map {i}")
+
+
+@pytest.mark.gpu
+def test_gpu_gather_l1_edge_cases():
+    from rtm3d_b200 import gather_l1_loss
+    dev = torch.device("cuda:0")
+    fmap = torch.randn(2, 4, 5, 6, device=dev, requires_grad=True)
+    z = lambda *s, dt=torch.int64: torch.zeros(s, dtype=dt, device=dev)
+    # nothing valid: mean over an empty selection is NaN (F.l1_loss), and the gradient call must not fault
+    loss = gather_l1_loss(fmap, z(3), z(3), z(3), torch.zeros(3, dtype=torch.bool, device=dev), torch.zeros(3, 2, device=dev))
+    assert torch.isnan(loss)
+    # out-of-map entries are skipped; the others count
+    img = torch.tensor([0, 1, 5], device=dev); x = torch.tensor([1, 7, 0], device=dev); y = torch.tensor([2, 0, 0], device=dev)
+    tgt = torch.tensor([[0.5, -0.5], [0.0, 0.0], [0.0, 0.0]], device=dev)
+    loss = gather_l1_loss(fmap, img, x, y, torch.ones(3, dtype=torch.bool, device=dev), tgt, c0=torch.tensor([2, 0, 0], device=dev, dtype=torch.int32))
+    want = ((fmap[0, 2, 2, 1] - 0.5).abs() + (fmap[0, 3, 2, 1] + 0.5).abs()) / 2
+    loss.backward()
+    assert torch.allclose(loss, want.detach(), rtol=1e-6)
+    assert int((fmap.grad != 0).sum()) == 2 and float(fmap.grad.abs().sum()) == pytest.approx(1.0, rel=1e-6)
