@@ -173,12 +173,14 @@ int rtm3d_abi_version(void) { return RTM3D_ABI_VERSION; }
 const char* rtm3d_last_error(void) { return g_err; }
 
 const char* rtm3d_build_info(void) {
-  return "librtm3d_decode: nvcc " __VERSION__ " cuda "
+  return "librtm3d_decode: host compiler " __VERSION__ ", nvcc "
 #define RTM3D_STR2(x) #x
 #define RTM3D_STR(x) RTM3D_STR2(x)
       RTM3D_STR(__CUDACC_VER_MAJOR__) "." RTM3D_STR(__CUDACC_VER_MINOR__)
-      " sm_100a; kernels: decode_planes (persistent, cp.async.bulk ring, histogram select), decode_generic (strip/merge),"
-      " group_vertices, box3d; fp32+bf16 inputs";
+      " sm_100a; kernels: scan_planes (persistent, plane-resident cp.async.bulk ring, verified order-statistic threshold),"
+      " select_post (cluster of 4 CTAs per image: register sort, epilogues, grouping, fused gather), select, decode_planes"
+      " (round-1 streaming kernel: planes larger than the ring), decode_generic (any shape), fit_box3d, box3d, target encoder,"
+      " focal + gather-L1 losses; fp32+bf16 head maps";
 }
 
 #ifdef RTM3D_DEV
