@@ -29,11 +29,19 @@ def test_workloads_are_the_baseline_configs():
     assert bench.WORKLOADS["cfg4"]["B"] == 256 and bench.WORKLOADS["cfg4"]["kpt"] == 9 and bench.WORKLOADS["cfg4"]["K"] == 100
     assert (bench.WORKLOADS["cfg5"]["H"], bench.WORKLOADS["cfg5"]["W"], bench.WORKLOADS["cfg5"]["B"]) == (192, 640, 128)
     assert bench.WORKLOADS["cfg2"]["B"] == 32 and bench.WORKLOADS["cfg2"]["K"] == 50
-    assert bench.WORKLOADS["cfg3"]["kpt"] == 0
+    assert bench.WORKLOADS["cfg3"]["kpt"] == 0 and bench.WORKLOADS["cfg3"]["reg"] == 8            # configs[2] as written: 8 regression channels
+    assert bench.WORKLOADS["cfg2x"]["B"] == 64 and bench.WORKLOADS["cfg2x"]["kpt"] == 9            # north_star's batch >= 64 point
+
+
+def test_per_kernel_bytes_add_up_to_the_step():
+    # scan kernel = the heat-maps, select + post kernel = gathers + outputs: together the algorithmic bytes of the step
+    w = _w(256, 96, 320, 100, 9)
+    kb = bench.kernel_bytes_per_image(w)
+    assert kb["scan"] == 12 * 96 * 320 * 4 and kb["scan"] + kb["post"] == bench.algorithmic_bytes_per_image(w)[0]
 
 
 def test_cli_lists_the_contract_flags():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0
-    for flag in ("--gpus", "--steps", "--warmup", "--impl", "--workload", "--dtype", "--no-e2e", "--max-ctas"):
+    for flag in ("--gpus", "--steps", "--warmup", "--impl", "--workload", "--dtype", "--no-e2e", "--max-ctas", "--scaling", "--gather", "--graph", "--verify"):
         assert flag in out.stdout, flag
