@@ -65,8 +65,10 @@ const char* rtm3d_last_error(void);
 /* static string: compiler, arch and kernel variants built in */
 const char* rtm3d_build_info(void);
 
-/* Bytes of device scratch the decode entry points need for this shape (the threshold table, keys of the per-strip
- * top-K lists, per-image tickets, remembered thresholds).  The scratch must be initialised ONCE with
+/* Bytes of device scratch the decode entry points need for this shape: the scan kernel's per-strip candidate lists
+ * (max(1024, 4K) 64-bit keys each) with their lengths, its strip-queue and completion counters, and -- for the shapes the
+ * round-1 kernels serve -- the threshold table, keys of the per-strip top-K lists, per-image tickets and remembered
+ * thresholds.  The scratch must be initialised ONCE with
  * rtm3d_workspace_init after allocation (zero fill + the table of logit bounds per score-histogram bin, 8 KB at the
  * start of the scratch); every call leaves it clean again (tickets are reset by the CTA that consumes them).  A scratch
  * that was only zeroed still gives identical results -- the kernels then compute the bounds themselves, more slowly.
