@@ -9,8 +9,10 @@ over one batch of synthetic head outputs that are already resident in HBM.  The 
 configs[3] ("cfg4": 256 images per GPU, 3x96x320 main heat-map + 9-keypoint heat-map + the 16/2/2-channel regression
 maps, K=100, thresh 0.4), the configuration the metric's "1/2/4/8 B200" is quoted on.  Images are independent
 (SURVEY.md 8e): `--scaling weak` (default) keeps 256 images per GPU as N grows, `--scaling strong` cuts the 256 images into
-N shards; for N > 1 the step ends with the NCCL all-gather of the fixed-size detections.  One JSON line is printed by
-rank 0 (contract in the task statement):
+N shards; for N > 1 every rank's fixed-size detections are delivered to every rank (`--gather`: rows left in the rank's own
+symmetric-memory buffer by the select + post kernel and moved by the copy engines on a second stream, rows stored by the
+kernel itself into every rank's buffer, or rtm3d_pack_wire + NCCL all-gather).  One JSON line is
+printed by rank 0 (contract in the task statement):
 
   value        whole-job images/s, device-timed (CUDA events around exactly K steps, max over ranks)
   roofline     per kernel: the bytes THAT kernel moves / its CUDA-event duration vs MEASURED_PEAKS.json hbm_gbs (the
@@ -355,10 +357,10 @@ def run_b200(args, w_job):
 
     def step(i, marks=None, inputs=None, graph=None):
         """One step.  N > 1: the decode on the launching stream (from a CUDA graph when given) and the path's one exchange
-        (SURVEY.md 8e), the gather of the fixed-size detections: fused into the select + post kernel (peer-to-peer stores,
-        then a barrier of the ranks on a second stream), or rtm3d_pack_wire + NCCL all-gather on the second stream -- either
-        way behind an event, so that the exchange of batch i overlaps the decode of batch i+1; the timed region ends with a
-        device-wide synchronise, i.e. with every exchange complete."""
+        (SURVEY.md 8e), the gather of the fixed-size detections: copy engines behind the kernel (ce), fused into the select +
+        post kernel (p2p / p2pd: peer-to-peer stores, arrival flags awaited on a second stream), or rtm3d_pack_wire + NCCL
+        all-gather on the second stream -- always behind an event, so that the exchange of batch i overlaps the decode of batch
+        i+1; the timed region ends behind the last exchange."""
         p2p = world > 1 and gather_out["mode"] in ("p2p", "p2pd", "ce")
         deferred = world > 1 and gather_out["mode"] == "p2pd"
         ce = world > 1 and gather_out["mode"] == "ce"
