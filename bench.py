@@ -637,9 +637,17 @@ def run_b200(args, w_job):
                          "step_achieved": round(step_gbs, 1), "step_frac": round(step_gbs / peak, 4),
                          "algorithmic_bytes_per_image": A, "cold_ms": None if cold_ms is None else round(cold_ms, 5),
                          "shift_ms_per_step": None if shift_ms is None else round(shift_ms, 5),
-                         "state": "none: thresholds come from each strip's own data (no memory across planes or launches)"},
+                         "frac_of_nominal_8tbs": round(per_kernel[dom]["gbs"] / 8000.0, 4),
+                         # every head map counted in full (the literal reading of north_star) -- NOT the headline:
+                         # nobody streams the regression planes, the decode gathers K points from them
+                         "literal_full_maps": {"gbs": round(B * (w["C"] + Cv + (w["reg"] if w.get("reg") else 20)) * w["H"] * w["W"] * elem
+                                                            / (ms_step * 1e-3) / 1e9, 1), "note": "all head maps in full / ms_per_step; not the headline"},
+                         "state": ("round-1 streaming kernels (planes larger than the scan kernel's ring): thresholds remembered per workspace"
+                                   if names[0].startswith("decode_planes") else
+                                   "none: thresholds come from each strip's own data (no memory across planes or launches)")},
             "e2e": e2e,
-            "gpu_launches": (n_launches + (1 if world > 1 and gather_out["mode"] == "nccl" else 0)) * args.steps,
+            # (+ per step at N > 1: the wire-packing kernel (nccl), the flag-wait kernel (p2p, p2pd), the signal and wait kernels (ce))
+            "gpu_launches": (n_launches + (0 if world == 1 else {"nccl": 1, "p2p": 1, "p2pd": 1, "ce": 2}[gather_out["mode"]])) * args.steps,
             "clocks": sampler.summary(t_wall0, t_wall1),
         }
         if cpu_baseline is not None:
